@@ -1,0 +1,133 @@
+/*
+ * vllm_ltr_b200.h — C ABI of libvllm_ltr_b200.so
+ *
+ * B200 (sm_100a) implementation of the decode-time hot path of hao-ai-lab/vllm-ltr.
+ * Every entry point replaces one function of the reference's pybind surface
+ * (csrc/pybind.cpp:6-125, declarations csrc/ops.h, csrc/cache.h, csrc/cuda_utils.h) or one
+ * piece of the LTR scheduling tick (vllm/core/scheduler.py, vllm/engine/aux_llm_engine.py).
+ * The signatures carry plain pointers, sizes, strides and a cudaStream_t (as void*): no
+ * torch types.  The Python module vllm_ltr_b200._C re-creates the reference's tensor-level
+ * surface (same names / argument order / error behaviour) on top of these calls.
+ *
+ * Conventions
+ *   - all device pointers are owned by the caller; ops write in place exactly like the
+ *     reference ops (out / caches / input+residual / query+key);
+ *   - every call returns 0 on success, a VLTR_ERR_* code otherwise; vltr_last_error()
+ *     returns a thread-local message (what TORCH_CHECK would have put in the RuntimeError);
+ *   - kernels are enqueued on `stream` (the caller passes torch's current stream) of the
+ *     current device; nothing synchronises unless stated;
+ *   - dtype codes: VLTR_F32 / VLTR_F16 / VLTR_BF16 for activations, kv_fp8 = 0 ("auto": cache
+ *     has the activation dtype) or 1 ("fp8": unscaled e5m2 bytes, kv_scale ignored on CUDA,
+ *     csrc/quantization/fp8_e5m2_kvcache/quant_utils.cuh:164-192).
+ */
+#ifndef VLLM_LTR_B200_H_
+#define VLLM_LTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLTR_OK 0
+#define VLTR_ERR_INVALID 1     /* argument rejected (reference: TORCH_CHECK(false, ...)) */
+#define VLTR_ERR_CUDA 2        /* CUDA runtime error at launch */
+#define VLTR_ERR_UNSUPPORTED 3 /* head size / block size / dtype outside the reference's grid */
+
+#define VLTR_F32 0
+#define VLTR_F16 1
+#define VLTR_BF16 2
+#define VLTR_U8 3
+
+const char* vltr_last_error(void);
+/* "sm_100a;<build id>" — lets callers assert the CUDA library (not a fallback) is loaded. */
+const char* vltr_build_info(void);
+/* number of kernel launches issued through this library since load (process-wide). */
+uint64_t vltr_launch_count(void);
+
+/* ---- attention: csrc/attention/attention_kernels.cu:741-778 (v1), :935-975 (v2) ------------
+ * out   [num_seqs, num_heads, head_size]            (contiguous)
+ * query [num_seqs, num_heads, head_size]            (row stride q_stride elements)
+ * key_cache   [num_blocks, num_kv_heads, head_size/x, block_size, x], x = 16/sizeof(cache elt)
+ * value_cache [num_blocks, num_kv_heads, head_size, block_size]
+ *             (kv_block_stride / kv_head_stride in elements; a (block, head) tile is contiguous)
+ * block_tables [num_seqs, max_num_blocks_per_seq] int32; context_lens [num_seqs] int32
+ * alibi_slopes [num_heads] float or NULL.
+ * v1 never needs caller scratch; when it decides to split long contexts it uses a library-owned
+ * workspace.  v2 uses the caller's exp_sums/max_logits [num_seqs,num_heads,max_num_partitions]
+ * float and tmp_out [num_seqs,num_heads,max_num_partitions,head_size] (activation dtype) with
+ * the reference's 512-token partitions, and leaves them filled exactly as the reference does. */
+int vltr_paged_attention_v1(void* out, const void* query, const void* key_cache,
+                            const void* value_cache, int num_seqs, int num_heads, int head_size,
+                            int num_kv_heads, float scale, const int32_t* block_tables,
+                            const int32_t* context_lens, int block_size, int max_context_len,
+                            int max_num_blocks_per_seq, const float* alibi_slopes,
+                            int64_t q_stride, int64_t kv_block_stride, int64_t kv_head_stride,
+                            int dtype, int kv_fp8, float kv_scale, void* stream);
+
+int vltr_paged_attention_v2(void* out, float* exp_sums, float* max_logits, void* tmp_out,
+                            const void* query, const void* key_cache, const void* value_cache,
+                            int num_seqs, int num_heads, int head_size, int num_kv_heads,
+                            float scale, const int32_t* block_tables,
+                            const int32_t* context_lens, int block_size, int max_context_len,
+                            int max_num_blocks_per_seq, const float* alibi_slopes,
+                            int64_t q_stride, int64_t kv_block_stride, int64_t kv_head_stride,
+                            int dtype, int kv_fp8, float kv_scale, void* stream);
+
+/* ---- cache ops: csrc/cache_kernels.cu ------------------------------------------------------
+ * reshape_and_cache (:235-276): key/value [num_tokens, num_heads, head_size] with row strides
+ * key_stride/value_stride (elements); slot_mapping [num_tokens] int64, slot < 0 skipped. */
+int vltr_reshape_and_cache(const void* key, const void* value, void* key_cache,
+                           void* value_cache, const int64_t* slot_mapping, int num_tokens,
+                           int num_heads, int head_size, int block_size, int x,
+                           int64_t key_stride, int64_t value_stride, int dtype, int kv_fp8,
+                           float kv_scale, void* stream);
+
+/* copy_blocks (:97-152): key_cache_ptrs/value_cache_ptrs are HOST arrays of num_layers device
+ * pointers; block_mapping is a HOST array of num_pairs (src,dst) int64 pairs in the reference's
+ * std::map iteration order.  block_bytes = bytes of one block of one layer's K (== V).
+ * No host<->device copy and no synchronisation (the reference does three blocking H2D). */
+int vltr_copy_blocks(void* const* key_cache_ptrs, void* const* value_cache_ptrs, int num_layers,
+                     const int64_t* block_mapping, int num_pairs, int64_t block_bytes,
+                     void* stream);
+
+/* swap_blocks (:23-62): src/dst base pointers of one layer's K or V cache on device or host.
+ * kind: 0 = D2D, 1 = D2H, 2 = H2D.  block_mapping: HOST array of num_pairs (src,dst) pairs.
+ * Pinned (device-mapped) host memory is moved by ONE gather/scatter kernel; pageable host
+ * memory takes one cudaMemcpyAsync per run of consecutive blocks. */
+int vltr_swap_blocks(const void* src, void* dst, int kind, const int64_t* block_mapping,
+                     int num_pairs, int64_t block_bytes, void* stream);
+
+/* convert_fp8 (:298-339): numel elements; exactly one of src/dst dtype is VLTR_U8. */
+int vltr_convert_fp8(const void* src, void* dst, int64_t numel, int src_dtype, int dst_dtype,
+                     void* stream);
+
+/* ---- layernorm: csrc/layernorm_kernels.cu:277-352 ---------------------------------------- */
+int vltr_rms_norm(void* out, const void* input, const void* weight, float epsilon,
+                  int num_tokens, int hidden_size, int dtype, void* stream);
+int vltr_fused_add_rms_norm(void* input, void* residual, const void* weight, float epsilon,
+                            int num_tokens, int hidden_size, int dtype, void* stream);
+
+/* ---- rotary: csrc/pos_encoding_kernels.cu:124-226 ------------------------------------------
+ * cos_sin_cache_offsets NULL -> rotary_embedding, else batched_rotary_embedding. */
+int vltr_rotary_embedding(const int64_t* positions, void* query, void* key, int64_t num_tokens,
+                          int num_heads, int num_kv_heads, int head_size, int rot_dim,
+                          int64_t query_stride, int64_t key_stride, const void* cos_sin_cache,
+                          const int64_t* cos_sin_cache_offsets, int is_neox, int dtype,
+                          void* stream);
+
+/* ---- activations: csrc/activation_kernels.cu:76-161 ----------------------------------------
+ * act: 0 silu_and_mul, 1 gelu_and_mul, 2 gelu_tanh_and_mul (input [tokens, 2d] -> out [tokens,d])
+ *      3 gelu_new, 4 gelu_fast                        (input [tokens, d]  -> out [tokens,d]) */
+int vltr_activation(void* out, const void* input, int64_t num_tokens, int d, int act, int dtype,
+                    void* stream);
+
+/* ---- cuda utils: csrc/cuda_utils_kernels.cu ---------------------------------------------- */
+int vltr_get_device_attribute(int attribute, int device_id);
+int vltr_get_max_shared_memory_per_block_device_attribute(int device_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLLM_LTR_B200_H_ */

@@ -1,0 +1,327 @@
+// cache.cu — reshape_and_cache, copy_blocks, swap_blocks, convert_fp8.
+//
+// Replaces csrc/cache_kernels.cu of the reference: swap_blocks :23-62, copy_blocks :68-152,
+// reshape_and_cache :157-276, convert_fp8 :281-339.  All are pure index/copy work and are
+// bit-exact with the reference (fp8 goes through the same cuda_fp8.h conversions).
+//
+// Paged layout (part of the ABI, vllm/attention/ops/paged_attn.py:42-61):
+//   key_cache   [num_blocks, num_kv_heads, head_size/x, block_size, x]   x = 16 / sizeof(cache elt)
+//   value_cache [num_blocks, num_kv_heads, head_size, block_size]
+//
+// B200 shape:
+//   reshape_and_cache — (token, head, 16-byte chunk) items flattened over the grid; the source is
+//     read with 128-bit loads, each K chunk is ONE 16-byte store (the layout keeps x elements of a
+//     token together), V is x scalar stores (the layout strides tokens by block_size).
+//   copy_blocks — layer pointers and (src,dst) pairs travel as kernel parameters (CUDA >= 12.1
+//     allows 32 KB of them): no pointer-array tensors, no blocking H2D copies (the reference does
+//     three per call, cache_kernels.cu:129-136), 128-bit copies, grid sized over
+//     (slab, layer*2, pair).
+//   swap_blocks — pinned host memory is device-mapped under UVA, so a swap of any number of
+//     blocks is ONE gather/scatter kernel over PCIe instead of one cudaMemcpyAsync per block
+//     (cache_kernels.cu:50-61); pageable memory falls back to memcpy per run of consecutive blocks.
+#include "common.cuh"
+
+namespace vltr {
+
+// ------------------------------------------------------------------------------------------------
+// reshape_and_cache
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename CT, bool FP8>
+__device__ __forceinline__ CT cache_cvt(T v) {
+  if constexpr (FP8)
+    return to_fp8<T>(v);
+  else
+    return v;
+}
+
+// vector path: one thread moves XE = 16/sizeof(CT) consecutive head elements of one token
+template <typename T, typename CT, bool FP8>
+__global__ void __launch_bounds__(256)
+    reshape_and_cache_vec_kernel(const T* __restrict__ key, const T* __restrict__ value,
+                                 CT* __restrict__ key_cache, CT* __restrict__ value_cache,
+                                 const int64_t* __restrict__ slot_mapping, int64_t key_stride,
+                                 int64_t value_stride, int num_heads, int head_size,
+                                 int block_size, int64_t num_items) {
+  constexpr int XE = 16 / sizeof(CT);              // == x
+  constexpr int LD = XE * sizeof(T) / 16;          // 16-byte loads per tensor per thread
+  constexpr int N = 16 / sizeof(T);
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= num_items) return;
+  const int chunks = head_size / XE;
+  const int chunk = (int)(item % chunks);
+  const int64_t th = item / chunks;
+  const int head = (int)(th % num_heads);
+  const int64_t token = th / num_heads;
+  const int64_t slot = slot_mapping[token];
+  if (slot < 0) return;  // padding token (cache_kernels.cu:172-175)
+  const int64_t blk = slot / block_size;
+  const int off = (int)(slot % block_size);
+
+  const T* ksrc = key + token * key_stride + (int64_t)head * head_size + chunk * XE;
+  const T* vsrc = value + token * value_stride + (int64_t)head * head_size + chunk * XE;
+  alignas(16) T kbuf[XE];
+  alignas(16) T vbuf[XE];
+#pragma unroll
+  for (int l = 0; l < LD; ++l) {
+    *reinterpret_cast<uint4*>(&kbuf[l * N]) = ld_nc_16(ksrc + l * N);
+    *reinterpret_cast<uint4*>(&vbuf[l * N]) = ld_nc_16(vsrc + l * N);
+  }
+  alignas(16) CT kout[XE];
+#pragma unroll
+  for (int e = 0; e < XE; ++e) kout[e] = cache_cvt<T, CT, FP8>(kbuf[e]);
+  const int64_t bh = blk * num_heads + head;
+  CT* kdst = key_cache + ((bh * chunks + chunk) * block_size + off) * XE;
+  st_16(kdst, *reinterpret_cast<uint4*>(kout));
+  CT* vdst = value_cache + (bh * head_size + chunk * XE) * block_size + off;
+#pragma unroll
+  for (int e = 0; e < XE; ++e) vdst[(int64_t)e * block_size] = cache_cvt<T, CT, FP8>(vbuf[e]);
+}
+
+// scalar path: one element per thread, any x / alignment
+template <typename T, typename CT, bool FP8>
+__global__ void __launch_bounds__(256)
+    reshape_and_cache_scalar_kernel(const T* __restrict__ key, const T* __restrict__ value,
+                                    CT* __restrict__ key_cache, CT* __restrict__ value_cache,
+                                    const int64_t* __restrict__ slot_mapping, int64_t key_stride,
+                                    int64_t value_stride, int num_heads, int head_size,
+                                    int block_size, int x, int64_t num_items) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= num_items) return;
+  const int n = num_heads * head_size;
+  const int i = (int)(item % n);
+  const int64_t token = item / n;
+  const int64_t slot = slot_mapping[token];
+  if (slot < 0) return;
+  const int64_t blk = slot / block_size;
+  const int off = (int)(slot % block_size);
+  const int head = i / head_size, ho = i % head_size;
+  const int x_idx = ho / x, x_off = ho % x;
+  const int64_t bh = blk * num_heads + head;
+  const int64_t kt = ((bh * (head_size / x) + x_idx) * block_size + off) * x + x_off;
+  const int64_t vt = (bh * head_size + ho) * block_size + off;
+  key_cache[kt] = cache_cvt<T, CT, FP8>(key[token * key_stride + i]);
+  value_cache[vt] = cache_cvt<T, CT, FP8>(value[token * value_stride + i]);
+}
+
+template <typename T, typename CT, bool FP8>
+int launch_reshape(const void* key, const void* value, void* key_cache, void* value_cache,
+                   const int64_t* slot_mapping, int num_tokens, int num_heads, int head_size,
+                   int block_size, int x, int64_t key_stride, int64_t value_stride,
+                   cudaStream_t stream) {
+  constexpr int XE = 16 / sizeof(CT);
+  constexpr int N = 16 / sizeof(T);
+  if (num_tokens == 0 || num_heads == 0 || head_size == 0) return VLTR_OK;
+  const bool vec_ok = x == XE && head_size % XE == 0 && key_stride % N == 0 &&
+                      value_stride % N == 0 && (uintptr_t)key % 16 == 0 &&
+                      (uintptr_t)value % 16 == 0 && (uintptr_t)key_cache % 16 == 0;
+  if (vec_ok) {
+    const int64_t items = (int64_t)num_tokens * num_heads * (head_size / XE);
+    reshape_and_cache_vec_kernel<T, CT, FP8><<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
+        (const T*)key, (const T*)value, (CT*)key_cache, (CT*)value_cache, slot_mapping,
+        key_stride, value_stride, num_heads, head_size, block_size, items);
+  } else {
+    const int64_t items = (int64_t)num_tokens * num_heads * head_size;
+    reshape_and_cache_scalar_kernel<T, CT, FP8>
+        <<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
+            (const T*)key, (const T*)value, (CT*)key_cache, (CT*)value_cache, slot_mapping,
+            key_stride, value_stride, num_heads, head_size, block_size, x, items);
+  }
+  VLTR_LAUNCH_CHECK("reshape_and_cache");
+  return VLTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block copies (copy_blocks / swap_blocks)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxBufs = 256;    // 2 * num_layers pointers per launch
+constexpr int kMaxPairs = 512;   // (src,dst) pairs per launch
+
+struct CopyParams {
+  const char* src[kMaxBufs];
+  char* dst[kMaxBufs];
+  int64_t pair_src[kMaxPairs];
+  int64_t pair_dst[kMaxPairs];
+  int64_t block_bytes;
+};
+
+// grid (slabs, bufs, pairs); each CTA copies a 16 KiB slab of one block of one buffer
+constexpr int kSlabBytes = 16384;
+__global__ void __launch_bounds__(256) block_copy_kernel(const __grid_constant__ CopyParams p) {
+  const char* src = p.src[blockIdx.y] + p.pair_src[blockIdx.z] * p.block_bytes;
+  char* dst = p.dst[blockIdx.y] + p.pair_dst[blockIdx.z] * p.block_bytes;
+  const int64_t begin = (int64_t)blockIdx.x * kSlabBytes;
+  const int64_t end = min(begin + (int64_t)kSlabBytes, p.block_bytes);
+  if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)p.block_bytes) & 15) == 0) {
+    uint4 v[4];
+    const int64_t o = begin + (int64_t)threadIdx.x * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (o + k * 4096 < end) v[k] = *reinterpret_cast<const uint4*>(src + o + k * 4096);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (o + k * 4096 < end) *reinterpret_cast<uint4*>(dst + o + k * 4096) = v[k];
+  } else {
+    for (int64_t o = begin + threadIdx.x; o < end; o += blockDim.x) dst[o] = src[o];
+  }
+}
+
+static int run_block_copies(const char* const* src, char* const* dst, int nbufs,
+                            const int64_t* mapping, int num_pairs, int64_t block_bytes,
+                            cudaStream_t stream, const char* name) {
+  if (nbufs == 0 || num_pairs == 0 || block_bytes == 0) return VLTR_OK;
+  const unsigned slabs = (unsigned)((block_bytes + kSlabBytes - 1) / kSlabBytes);
+  for (int b0 = 0; b0 < nbufs; b0 += kMaxBufs) {
+    const int nb = nbufs - b0 < kMaxBufs ? nbufs - b0 : kMaxBufs;
+    for (int p0 = 0; p0 < num_pairs; p0 += kMaxPairs) {
+      const int np = num_pairs - p0 < kMaxPairs ? num_pairs - p0 : kMaxPairs;
+      CopyParams p;
+      for (int i = 0; i < nb; ++i) {
+        p.src[i] = src[b0 + i];
+        p.dst[i] = dst[b0 + i];
+      }
+      for (int i = 0; i < np; ++i) {
+        p.pair_src[i] = mapping[2 * (p0 + i)];
+        p.pair_dst[i] = mapping[2 * (p0 + i) + 1];
+      }
+      p.block_bytes = block_bytes;
+      block_copy_kernel<<<dim3(slabs, nb, np), 256, 0, stream>>>(p);
+      VLTR_LAUNCH_CHECK(name);
+    }
+  }
+  return VLTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// convert_fp8
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    to_fp8_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = to_fp8<T>(src[i]);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+    from_fp8_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = from_fp8<T>(src[i]);
+}
+
+}  // namespace vltr
+
+extern "C" int vltr_reshape_and_cache(const void* key, const void* value, void* key_cache,
+                                      void* value_cache, const int64_t* slot_mapping,
+                                      int num_tokens, int num_heads, int head_size,
+                                      int block_size, int x, int64_t key_stride,
+                                      int64_t value_stride, int dtype, int kv_fp8, float kv_scale,
+                                      void* stream) {
+  using namespace vltr;
+  (void)kv_scale;  // unscaled e5m2: ignored on CUDA, as in the reference
+  VLTR_CHECK(num_tokens >= 0 && num_heads >= 0 && head_size >= 0, VLTR_ERR_INVALID,
+             "reshape_and_cache: negative size");
+  VLTR_CHECK(block_size > 0 && x > 0 && head_size % x == 0, VLTR_ERR_INVALID,
+             "reshape_and_cache: block_size %d / x %d invalid for head_size %d", block_size, x,
+             head_size);
+  cudaStream_t s = (cudaStream_t)stream;
+  VLTR_DISPATCH_FLOAT(dtype, "reshape_and_cache", {
+    if (kv_fp8)
+      return launch_reshape<scalar_t, uint8_t, true>(key, value, key_cache, value_cache,
+                                                     slot_mapping, num_tokens, num_heads,
+                                                     head_size, block_size, x, key_stride,
+                                                     value_stride, s);
+    return launch_reshape<scalar_t, scalar_t, false>(key, value, key_cache, value_cache,
+                                                     slot_mapping, num_tokens, num_heads,
+                                                     head_size, block_size, x, key_stride,
+                                                     value_stride, s);
+  });
+  return VLTR_OK;
+}
+
+extern "C" int vltr_copy_blocks(void* const* key_cache_ptrs, void* const* value_cache_ptrs,
+                                int num_layers, const int64_t* block_mapping, int num_pairs,
+                                int64_t block_bytes, void* stream) {
+  using namespace vltr;
+  VLTR_CHECK(num_layers >= 0 && num_pairs >= 0 && block_bytes >= 0, VLTR_ERR_INVALID,
+             "copy_blocks: negative size");
+  if (num_layers == 0 || num_pairs == 0) return VLTR_OK;
+  // one buffer list: K of every layer then V of every layer; src and dst are the same cache
+  const int nbufs = 2 * num_layers;
+  const char** src = (const char**)alloca(sizeof(char*) * nbufs);
+  char** dst = (char**)alloca(sizeof(char*) * nbufs);
+  for (int l = 0; l < num_layers; ++l) {
+    src[l] = dst[l] = (char*)key_cache_ptrs[l];
+    src[num_layers + l] = dst[num_layers + l] = (char*)value_cache_ptrs[l];
+  }
+  return run_block_copies(src, dst, nbufs, block_mapping, num_pairs, block_bytes,
+                          (cudaStream_t)stream, "copy_blocks");
+}
+
+extern "C" int vltr_swap_blocks(const void* src, void* dst, int kind,
+                                const int64_t* block_mapping, int num_pairs, int64_t block_bytes,
+                                void* stream) {
+  using namespace vltr;
+  VLTR_CHECK(kind >= 0 && kind <= 2, VLTR_ERR_INVALID, "swap_blocks: Invalid device combination");
+  VLTR_CHECK(num_pairs >= 0 && block_bytes >= 0, VLTR_ERR_INVALID, "swap_blocks: negative size");
+  if (num_pairs == 0 || block_bytes == 0) return VLTR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool mapped = true;
+  if (kind != 0) {
+    // the host side must be pinned (cudaHostAlloc / cudaHostRegister) to be read by a kernel
+    const void* host = kind == 1 ? dst : src;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, host);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      mapped = false;
+    } else {
+      mapped = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+      if (mapped) {
+        if (kind == 1)
+          dst = (char*)attr.devicePointer;
+        else
+          src = (const char*)attr.devicePointer;
+      }
+    }
+  }
+  if (mapped) {
+    const char* sp = (const char*)src;
+    char* dp = (char*)dst;
+    return run_block_copies(&sp, &dp, 1, block_mapping, num_pairs, block_bytes, s, "swap_blocks");
+  }
+  // pageable host memory: cudaMemcpyAsync per run of consecutive (src,dst) blocks
+  const cudaMemcpyKind mk = kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+  int i = 0;
+  while (i < num_pairs) {
+    int j = i + 1;
+    while (j < num_pairs && block_mapping[2 * j] == block_mapping[2 * (j - 1)] + 1 &&
+           block_mapping[2 * j + 1] == block_mapping[2 * (j - 1) + 1] + 1)
+      ++j;
+    VLTR_CUDA(cudaMemcpyAsync((char*)dst + block_mapping[2 * i + 1] * block_bytes,
+                              (const char*)src + block_mapping[2 * i] * block_bytes,
+                              (size_t)(j - i) * block_bytes, mk, s));
+    i = j;
+  }
+  return VLTR_OK;
+}
+
+extern "C" int vltr_convert_fp8(const void* src, void* dst, int64_t numel, int src_dtype,
+                                int dst_dtype, void* stream) {
+  using namespace vltr;
+  VLTR_CHECK(numel >= 0, VLTR_ERR_INVALID, "convert_fp8: negative size");
+  VLTR_CHECK((src_dtype == VLTR_U8) != (dst_dtype == VLTR_U8), VLTR_ERR_INVALID,
+             "convert_fp8: exactly one of src/dst must be the fp8 (uint8) cache");
+  if (numel == 0) return VLTR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((numel + 255) / 256);
+  if (dst_dtype == VLTR_U8) {
+    VLTR_DISPATCH_FLOAT(src_dtype, "convert_fp8", {
+      to_fp8_kernel<scalar_t><<<grid, 256, 0, s>>>((const scalar_t*)src, (uint8_t*)dst, numel);
+    });
+  } else {
+    VLTR_DISPATCH_FLOAT(dst_dtype, "convert_fp8", {
+      from_fp8_kernel<scalar_t><<<grid, 256, 0, s>>>((const uint8_t*)src, (scalar_t*)dst, numel);
+    });
+  }
+  VLTR_LAUNCH_CHECK("convert_fp8");
+  return VLTR_OK;
+}

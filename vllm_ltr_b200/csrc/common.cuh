@@ -1,0 +1,168 @@
+// common.cuh — shared helpers for libvllm_ltr_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/vllm_ltr_b200.h"
+
+namespace vltr {
+
+// ---- error reporting (thread-local message, reference: TORCH_CHECK -> RuntimeError) ----------
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define VLTR_CHECK(cond, code, ...)                 \
+  do {                                              \
+    if (!(cond)) return ::vltr::fail(code, __VA_ARGS__); \
+  } while (0)
+
+// call after every <<<>>>: counts the launch and converts a launch failure into an error code
+#define VLTR_LAUNCH_CHECK(name)                                                        \
+  do {                                                                                 \
+    ::vltr::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    cudaError_t e__ = cudaPeekAtLastError();                                           \
+    if (e__ != cudaSuccess) {                                                          \
+      cudaGetLastError();                                                              \
+      return ::vltr::fail(VLTR_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__));     \
+    }                                                                                  \
+  } while (0)
+
+#define VLTR_CUDA(call)                                                                \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return ::vltr::fail(VLTR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));    \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- scalar type traits -----------------------------------------------------------------------
+// The reference computes "in T": every c10::Half / c10::BFloat16 operator converts to float,
+// applies the op and rounds back (RN).  to_f / from_f are those two conversions.
+template <typename T>
+struct ST;
+template <>
+struct ST<float> {
+  static constexpr int code = VLTR_F32;
+  __device__ __forceinline__ static float to_f(float x) { return x; }
+  __device__ __forceinline__ static float from_f(float x) { return x; }
+};
+template <>
+struct ST<__half> {
+  static constexpr int code = VLTR_F16;
+  __device__ __forceinline__ static float to_f(__half x) { return __half2float(x); }
+  __device__ __forceinline__ static __half from_f(float x) { return __float2half_rn(x); }
+};
+template <>
+struct ST<__nv_bfloat16> {
+  static constexpr int code = VLTR_BF16;
+  __device__ __forceinline__ static float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+  __device__ __forceinline__ static __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+};
+
+// round-trip through T: the value a reference expression "(scalar_t)(expr)" would hold, as float
+template <typename T>
+__device__ __forceinline__ float rt(float x) {
+  return ST<T>::to_f(ST<T>::from_f(x));
+}
+
+// 16-byte vector of T
+template <typename T>
+struct alignas(16) Vec16 {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+
+__device__ __forceinline__ uint4 ld_nc_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_16(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// ---- fp8 e5m2 (unscaled), csrc/quantization/fp8_e5m2_kvcache/quant_utils.cuh -----------------
+// to fp8: saturate-to-finite RN conversion from the activation type (float / half / bf16 each
+// have their own direct intrinsic in the reference, :164-192); from fp8: via half (:24-30),
+// bf16 goes fp8 -> half -> float -> bf16 (:71-82).
+template <typename T>
+__device__ __forceinline__ uint8_t to_fp8(T x);
+template <>
+__device__ __forceinline__ uint8_t to_fp8<float>(float x) {
+  return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E5M2);
+}
+template <>
+__device__ __forceinline__ uint8_t to_fp8<__half>(__half x) {
+  return (uint8_t)__nv_cvt_halfraw_to_fp8(static_cast<__half_raw>(x), __NV_SATFINITE, __NV_E5M2);
+}
+template <>
+__device__ __forceinline__ uint8_t to_fp8<__nv_bfloat16>(__nv_bfloat16 x) {
+  return (uint8_t)__nv_cvt_bfloat16raw_to_fp8(static_cast<__nv_bfloat16_raw>(x), __NV_SATFINITE,
+                                              __NV_E5M2);
+}
+// e5m2 is the upper byte of an IEEE half: the reference's __nv_cvt_fp8_to_halfraw(a, __NV_E5M2)
+// is exactly (a << 8).
+__device__ __forceinline__ __half fp8_to_half(uint8_t a) {
+  return __ushort_as_half((unsigned short)((unsigned short)a << 8));
+}
+template <typename T>
+__device__ __forceinline__ T from_fp8(uint8_t a);
+template <>
+__device__ __forceinline__ float from_fp8<float>(uint8_t a) {
+  return __half2float(fp8_to_half(a));
+}
+template <>
+__device__ __forceinline__ __half from_fp8<__half>(uint8_t a) {
+  return fp8_to_half(a);
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_fp8<__nv_bfloat16>(uint8_t a) {
+  return __float2bfloat16(__half2float(fp8_to_half(a)));
+}
+
+}  // namespace vltr
+
+// dtype dispatch over the three activation types
+#define VLTR_DISPATCH_FLOAT(dtype, NAME, ...)                                   \
+  switch (dtype) {                                                              \
+    case VLTR_F32: {                                                            \
+      using scalar_t = float;                                                   \
+      __VA_ARGS__;                                                              \
+      break;                                                                    \
+    }                                                                           \
+    case VLTR_F16: {                                                            \
+      using scalar_t = __half;                                                  \
+      __VA_ARGS__;                                                              \
+      break;                                                                    \
+    }                                                                           \
+    case VLTR_BF16: {                                                           \
+      using scalar_t = __nv_bfloat16;                                           \
+      __VA_ARGS__;                                                              \
+      break;                                                                    \
+    }                                                                           \
+    default:                                                                    \
+      return ::vltr::fail(VLTR_ERR_UNSUPPORTED, "%s: Unsupported data type: %d", NAME, dtype); \
+  }

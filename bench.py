@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py - decode hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
+
+Metric (BASELINE.json): output tokens/s on a ShareGPT-shaped trace.  One "step" = one engine
+decode step of the hot path for a batch of B running sequences (one new token each): for every
+decoder layer  fused_add_rms_norm -> rotary_embedding -> reshape_and_cache -> paged_attention ->
+fused_add_rms_norm -> silu_and_mul, then the final norm (vllm_ltr_b200/hotpath.py; the cuBLAS
+GEMMs between them are library code outside this path and are NOT executed or counted).
+Contexts are the running contexts of a synthetic ShareGPT-shaped trace.
+
+  value     tokens/s with every input already resident in HBM (CUDA events, max over ranks)
+  e2e       the same step driven from HOST buffers: per step the engine's host-built inputs
+            (positions, slot_mapping, block_tables, context_lens, token hidden rows) are copied
+            from pinned memory, and the final-norm output is read back, inside the timed region
+  roofline  paged attention (the dominant kernel): algorithmic bytes per call / mean call time
+  cpu_baseline / --impl reference: the reference's own CPU kernels (csrc/cpu, built into
+            oracle/_ref by oracle/Makefile) driven through the same call sequence on host cores.
+
+N > 1 (torchrun): tensor-parallel shards of the same model (q/kv heads and MLP width divided,
+two all-reduces of [B, hidden] per layer over NCCL), scaling = "strong".
+"""
+import argparse
+import glob
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+# ---------------------------------------------------------------------------------------------
+# workload: running contexts of the synthetic ShareGPT-shaped trace
+# ---------------------------------------------------------------------------------------------
+def trace_contexts(batch: int, seed: int = 0, max_ctx: int = 8192):
+    rng = np.random.default_rng(seed)
+    prompt = np.clip(np.rint(np.exp(rng.normal(5.0, 1.0, batch))), 4, 2048).astype(np.int64)
+    out = np.clip(np.rint(np.exp(rng.normal(5.3, 1.1, batch))), 4, max_ctx - prompt).astype(np.int64)
+    done = (rng.random(batch) * out).astype(np.int64)       # tokens generated so far
+    ctx = np.minimum(prompt + done + 1, max_ctx)            # context seen by this decode step
+    return ctx
+
+
+def build_inputs(ctx: np.ndarray, block_size: int, num_blocks: int, seed: int):
+    """Host-side step inputs exactly as ModelRunner._prepare_decode builds them
+    (vllm/worker/model_runner.py:424-548): positions, slot_mapping, padded block_tables,
+    context_lens.  Block ids are a random permutation of the pool (worst-case locality)."""
+    rng = np.random.default_rng(seed + 1)
+    B = len(ctx)
+    nblk = (ctx + block_size - 1) // block_size
+    assert int(nblk.sum()) <= num_blocks
+    perm = rng.permutation(num_blocks)[: int(nblk.sum())]
+    mb = int(nblk.max())
+    bt = np.zeros((B, mb), dtype=np.int32)
+    o = 0
+    for i in range(B):
+        bt[i, : nblk[i]] = perm[o:o + nblk[i]]
+        o += nblk[i]
+    pos = (ctx - 1).astype(np.int64)
+    slot = bt[np.arange(B), pos // block_size].astype(np.int64) * block_size + pos % block_size
+    return dict(positions=torch.from_numpy(pos), slot_mapping=torch.from_numpy(slot),
+                block_tables=torch.from_numpy(bt),
+                context_lens=torch.from_numpy(ctx.astype(np.int32)))
+
+
+def attention_bytes(ctx, shape, block_size):
+    """Algorithmic bytes of one paged-attention call."""
+    s_cache = 1 if shape.kv_cache_dtype == "fp8" else torch.tensor([], dtype=shape.dtype).element_size()
+    s_act = torch.tensor([], dtype=shape.dtype).element_size()
+    B = len(ctx)
+    kv = int(ctx.sum()) * 2 * shape.kv_heads * shape.head_size * s_cache
+    qo = 2 * B * shape.q_heads * shape.head_size * s_act
+    tbl = 4 * int(((ctx + block_size - 1) // block_size).sum()) + 4 * B
+    return kv + qo + tbl
+
+
+def step_bytes(ctx, shape, block_size, layers):
+    """Algorithmic bytes of the whole step (all in-scope ops)."""
+    s = torch.tensor([], dtype=shape.dtype).element_size()
+    s_cache = 1 if shape.kv_cache_dtype == "fp8" else s
+    T, H, D = len(ctx), shape.hidden, shape.head_size
+    per_layer = (attention_bytes(ctx, shape, block_size)
+                 + 2 * (T * H * s * 4 + H * s)                                  # 2 fused norms
+                 + T * (shape.q_heads + shape.kv_heads) * D * s * 2 + T * D * s + 8 * T   # rope
+                 + T * 2 * shape.kv_heads * D * (s + s_cache) + 8 * T           # reshape_and_cache
+                 + T * shape.inter * s * 3)                                     # silu_and_mul
+    return per_layer * layers + T * H * s * 4 + H * s
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference CPU arm
+# ---------------------------------------------------------------------------------------------
+def load_ref_cpu():
+    """The reference's own CPU kernels (csrc/cpu/*.cpp), prebuilt into oracle/_ref by
+    oracle/Makefile.  Returns (module, kind)."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    stems = (["ref_cpu_C"] if "avx512_bf16" in flags else []) + ["ref_cpu_nobf16_C"]
+    if "avx512f" not in flags:
+        stems = []
+    for stem in stems:
+        hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", stem + ".*.so"))
+        if hits:
+            spec = importlib.util.spec_from_file_location(stem, hits[0])
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod, "reference"
+    return None, "port"
+
+
+class OraclePort:
+    """oracle/kernels.py dressed as a vllm._C module (used only when oracle/_ref is missing)."""
+
+    def __init__(self):
+        from oracle import kernels as K
+        port = self
+
+        class Ops:
+            @staticmethod
+            def rms_norm(out, x, w, eps):
+                out.copy_(K.rms_norm(x, w, eps))
+
+            @staticmethod
+            def fused_add_rms_norm(x, r, w, eps):
+                a, b = K.fused_add_rms_norm(x, r, w, eps)
+                x.copy_(a)
+                r.copy_(b)
+
+            @staticmethod
+            def rotary_embedding(pos, q, k, hs, cache, neox):
+                a, b = K.rotary_embedding(pos, q, k, hs, cache, neox)
+                q.copy_(a)
+                k.copy_(b)
+
+            @staticmethod
+            def silu_and_mul(out, x):
+                out.copy_(K.activation(x, "silu_and_mul"))
+
+            @staticmethod
+            def paged_attention_v1(out, q, kc, vc, hkv, scale, bt, cl, bs, mx, alibi, kvd, kvs):
+                out.copy_(K.paged_attention(q, kc, vc, bt, cl, scale, alibi, kvd).to(out.dtype))
+
+            paged_attention_v2 = None
+
+        class CacheOps:
+            @staticmethod
+            def reshape_and_cache(k, v, kc, vc, slots, kvd, kvs):
+                K.reshape_and_cache(k, v, kc, vc, slots, kvd)
+
+        self.ops, self.cache_ops = Ops, CacheOps
+
+
+def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_batch):
+    """Times the reference CPU kernels on a bounded sample: `sample_batch` sequences of the same
+    trace x `sample_layers` layers per step, scaled to the full layer count.  Returns
+    (tokens/s, ms per full step, description, cores, kind)."""
+    from vllm_ltr_b200.hotpath import DecodeHotPath, ModelShape
+    mod, kind = load_ref_cpu()
+    if mod is None:
+        mod = OraclePort()
+        sample_batch = min(sample_batch, 8)
+        sample_layers = 1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cshape = ModelShape(**{**shape.__dict__})
+    if cshape.dtype == torch.float16:
+        cshape.dtype = torch.bfloat16        # csrc/cpu implements f32 and bf16 only
+    cshape.kv_cache_dtype = "auto"            # and has no fp8 cache
+    sctx = ctx[:sample_batch]
+    bs = cshape.block_size
+    need = int(((sctx + bs - 1) // bs).sum())
+    hp = DecodeHotPath(cshape, need + 8, len(sctx), "cpu", seed=0, layers=sample_layers, C=mod)
+    inp = build_inputs(sctx, bs, need + 8, 0)
+    hidden = torch.randn(len(sctx), cshape.hidden).to(cshape.dtype)
+    mx = int(sctx.max())
+
+    def one():
+        hp.step(hidden, inp["positions"], inp["slot_mapping"], inp["block_tables"],
+                inp["context_lens"], mx)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    full = dt * shape.layers / sample_layers
+    tps = len(sctx) / full
+    desc = (f"{len(sctx)} of {len(ctx)} sequences of the trace x {sample_layers} of {shape.layers} "
+            f"layers per step, time scaled by {shape.layers}/{sample_layers}; "
+            f"csrc/cpu kernels ({'oracle/_ref' if kind == 'reference' else 'oracle port'}), "
+            f"{str(cshape.dtype).split('.')[-1]}, OMP threads={cores}")
+    return tps, full * 1e3, desc, cores, kind
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-2-7b")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-layers", type=int, default=2)
+    ap.add_argument("--cpu-sample-batch", type=int, default=256)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from vllm_ltr_b200.hotpath import SHAPES, ModelShape
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    full_shape = SHAPES[args.model]
+    # the reference CPU kernels have no fp16: the benchmark computes in bf16 on both arms
+    bench_shape = ModelShape(**{**full_shape.__dict__})
+    if bench_shape.dtype == torch.float16:
+        bench_shape.dtype = torch.bfloat16
+    if args.layers:
+        bench_shape.layers = args.layers
+    ctx = trace_contexts(args.batch)
+    workload = (f"{args.model} decode hot path (a1-a7: rms_norm/fused_add_rms_norm, rotary, "
+                f"reshape_and_cache, paged_attention, silu_and_mul x {bench_shape.layers} layers; "
+                f"GEMMs excluded), B={args.batch} running sequences of the synthetic ShareGPT "
+                f"trace (contexts mean {ctx.mean():.0f}, max {ctx.max()}), block 16")
+    config = {"workload": workload, "batch": args.batch, "layers": bench_shape.layers,
+              "sum_context_tokens": int(ctx.sum()), "parallelism": f"tp{world}",
+              "l2": "inputs larger than L2 (each layer reads its own KV pool)"}
+
+    # ---------------- reference arm: CPU kernels on host cores, rank 0 only ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        tps, ms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, args.steps,
+                                                       args.warmup, args.cpu_sample_layers,
+                                                       args.cpu_sample_batch)
+        print(json.dumps({
+            "impl": "reference", "metric": "output_tokens_per_s", "value": tps,
+            "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind,
+                             "sample": desc},
+            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ---------------- our arm ----------------
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    import torch.distributed as dist
+    from vllm_ltr_b200._lib import launch_count
+    from vllm_ltr_b200.hotpath import DecodeHotPath
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    shape = bench_shape.shard(world)
+    bs = shape.block_size
+    need = int(((ctx + bs - 1) // bs).sum())
+    num_blocks = need + 64
+    hp = DecodeHotPath(shape, num_blocks, args.batch, dev, seed=rank)
+    host = build_inputs(ctx, bs, num_blocks, 0)
+    max_ctx = int(ctx.max())
+    g = torch.Generator().manual_seed(0)
+    host["hidden"] = (torch.randn(args.batch, shape.hidden, generator=g) * 0.5).to(shape.dtype)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    out_host = torch.empty(args.batch, shape.hidden, dtype=shape.dtype).pin_memory()
+
+    all_reduce = None
+    if world > 1:
+        from vllm_ltr_b200.parallel import tensor_model_parallel_all_reduce
+        all_reduce = tensor_model_parallel_all_reduce
+
+    def step_resident():
+        return hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                       devin["block_tables"], devin["context_lens"], max_ctx, all_reduce)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        out = hp.step(d["hidden"], d["positions"], d["slot_mapping"], d["block_tables"],
+                      d["context_lens"], max_ctx, all_reduce)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the engine samples from this result
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # timed region 1: inputs resident, device time
+    hp.attn_events = []
+    n0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    t_end = time.time()
+    launches = launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
+    hp.attn_events = None
+
+    # timed region 2: host buffers in, result out, every step
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    clk = clocks.summary(t_start, t_end)
+    clocks.stop()
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    ms_per_step = ms / args.steps
+    tokens_per_s = args.batch / (ms_per_step * 1e-3)
+    e2e_tps = args.batch * args.steps / e2e_s
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+    abytes = attention_bytes(ctx, shape, bs)
+    attn_mean_ms = float(np.mean(attn_ms)) if attn_ms else float("nan")
+    achieved = abytes / (attn_mean_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "attention_traffic.json"))).get(
+            f"{args.model}-b{args.batch}-tp{world}")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "paged_attention (v1 entry; per call, incl. the merge "
+                "kernel when the library splits contexts)", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
+                "launch_ms_mean": attn_mean_ms, "launches_timed": len(attn_ms),
+                "attention_share_of_step": float(np.sum(attn_ms)) / ms if attn_ms else None,
+                "step_achieved_gbs": step_bytes(ctx, shape, bs, shape.layers) / (ms_per_step * 1e-3) / 1e9}
+
+    line = {
+        "metric": "output_tokens_per_s", "value": tokens_per_s, "unit": "tokens/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": config, "clocks": clk,
+        "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        tps, cms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, 2, 1,
+                                                        args.cpu_sample_layers,
+                                                        args.cpu_sample_batch)
+        line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind,
+                                "sample": desc, "ms_per_step": cms}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,8 @@ def fp8_e5m2_from(x: torch.Tensor) -> torch.Tensor:
 
     Round-to-nearest-even on the e5m2 grid, computed from the exact value (float64), saturating
     finite overflow to +-57344 (0x7B); NaN -> 0x7F|sign; inf saturates too (SATFINITE)."""
-    v = x.to(torch.float64).numpy()
+    dev = x.device
+    v = x.detach().to("cpu", torch.float64).numpy()
     out = np.zeros(v.shape, dtype=np.uint8)
     sign = (np.signbit(v)).astype(np.uint8) << 7
     a = np.abs(v)
@@ -62,7 +63,18 @@ def fp8_e5m2_from(x: torch.Tensor) -> torch.Tensor:
     code = np.where(normal, (e2 + 15).astype(np.int64) << 2, 0) + man.astype(np.int64)
     out = (code.astype(np.uint8) | sign).astype(np.uint8)
     out = np.where(nan, (0x7F | sign).astype(np.uint8), out)
-    return torch.from_numpy(out.astype(np.uint8))
+    return torch.from_numpy(out.astype(np.uint8)).to(dev)
+
+
+def fp8_e5m2_from_fast(x: torch.Tensor) -> torch.Tensor:
+    """Same conversion through torch's float8_e5m2 cast (RNE, but overflow -> inf/NaN), made
+    saturating by clamping finite values to +-57344 first.  Device-agnostic; pinned against
+    fp8_e5m2_from over all 65536 half bit patterns in tests/test_oracle.py."""
+    f = x.to(torch.float32)
+    f = torch.where(torch.isnan(f), f, f.clamp(-57344.0, 57344.0))
+    # round directly from the source type when it is narrower than float (no double rounding:
+    # half/bf16 -> float is exact)
+    return f.to(torch.float8_e5m2).view(torch.uint8)
 
 
 def fp8_e5m2_to(b: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -225,7 +237,9 @@ def paged_attention(query: torch.Tensor, key_cache: torch.Tensor, value_cache: t
     B, Hq, D = query.shape
     nb, Hkv, Dx, bs, x = key_cache.shape
     G = Hq // Hkv
-    out = torch.zeros(B, Hq, D, dtype=torch.float32)
+    dev = query.device
+    out = torch.zeros(B, Hq, D, dtype=torch.float32, device=dev)
+    context_lens = context_lens.to("cpu")
     if kv_cache_dtype == "fp8":
         key_cache = fp8_e5m2_to(key_cache, torch.float32)
         value_cache = fp8_e5m2_to(value_cache, torch.float32)
@@ -243,13 +257,63 @@ def paged_attention(query: torch.Tensor, key_cache: torch.Tensor, value_cache: t
         v = v.repeat_interleave(G, dim=1)
         logits = scale * torch.einsum("hd,lhd->hl", q64[i], k)
         if alibi_slopes is not None:
-            pos = torch.arange(L, dtype=torch.float64) - L + 1     # (:248)
+            pos = torch.arange(L, dtype=torch.float64, device=dev) - L + 1     # (:248)
             logits = logits + alibi_slopes.to(torch.float64)[:, None] * pos[None, :]
         m = logits.max(dim=1, keepdim=True).values
         e = torch.exp(logits - m)
         p = e / (e.sum(dim=1, keepdim=True) + 1e-6)
         out[i] = torch.einsum("hl,lhd->hd", p, v).to(torch.float32)
     return out
+
+
+def paged_attention_partitions(query: torch.Tensor, key_cache: torch.Tensor,
+                               value_cache: torch.Tensor, block_tables: torch.Tensor,
+                               context_lens: torch.Tensor, scale: float, partition_size: int = 512,
+                               alibi_slopes: Optional[torch.Tensor] = None,
+                               kv_cache_dtype: str = "auto"):
+    """What paged_attention_v2_kernel leaves in its side outputs (:382-441): for every partition
+    j of 512 tokens that intersects the context, max_logits[i,h,j] = max of the (scaled, biased)
+    logits, exp_sums[i,h,j] = sum exp(logit - max), tmp_out[i,h,j] = softmax-weighted V with the
+    partition-local denominator (exp_sum + 1e-6).  Entries of partitions past the context are
+    NaN here (the reference never writes them).  Returns float32 (max_logits, exp_sums, tmp_out)."""
+    B, Hq, D = query.shape
+    nb, Hkv, Dx, bs, x = key_cache.shape
+    G = Hq // Hkv
+    dev = query.device
+    context_lens = context_lens.to("cpu")
+    max_ctx = int(context_lens.max()) if B else 0
+    P = max(1, (max_ctx + partition_size - 1) // partition_size)
+    ml = torch.full((B, Hq, P), float("nan"), dtype=torch.float32, device=dev)
+    es = torch.full((B, Hq, P), float("nan"), dtype=torch.float32, device=dev)
+    to = torch.full((B, Hq, P, D), float("nan"), dtype=torch.float32, device=dev)
+    if kv_cache_dtype == "fp8":
+        key_cache = fp8_e5m2_to(key_cache, torch.float32)
+        value_cache = fp8_e5m2_to(value_cache, torch.float32)
+    q64 = query.to(torch.float64)
+    for i in range(B):
+        L = int(context_lens[i])
+        if L == 0:
+            continue
+        nblk = (L + bs - 1) // bs
+        ids = block_tables[i, :nblk].to(torch.int64)
+        k = key_cache[ids].permute(0, 3, 1, 2, 4).reshape(nblk * bs, Hkv, D)[:L].to(torch.float64)
+        v = value_cache[ids].permute(0, 3, 1, 2).reshape(nblk * bs, Hkv, D)[:L].to(torch.float64)
+        k = k.repeat_interleave(G, dim=1)
+        v = v.repeat_interleave(G, dim=1)
+        logits = scale * torch.einsum("hd,lhd->hl", q64[i], k)
+        if alibi_slopes is not None:
+            pos = torch.arange(L, dtype=torch.float64, device=dev) - L + 1
+            logits = logits + alibi_slopes.to(torch.float64)[:, None] * pos[None, :]
+        for j in range((L + partition_size - 1) // partition_size):
+            lo, hi = j * partition_size, min(L, (j + 1) * partition_size)
+            lg = logits[:, lo:hi]
+            m = lg.max(dim=1, keepdim=True).values
+            e = torch.exp(lg - m)
+            s = e.sum(dim=1, keepdim=True)
+            ml[i, :, j] = m[:, 0].to(torch.float32)
+            es[i, :, j] = s[:, 0].to(torch.float32)
+            to[i, :, j] = torch.einsum("hl,lhd->hd", e / (s + 1e-6), v[lo:hi]).to(torch.float32)
+    return ml, es, to
 
 
 def make_kv_cache(num_blocks: int, block_size: int, num_kv_heads: int, head_size: int,

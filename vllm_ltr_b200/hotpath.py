@@ -1,0 +1,217 @@
+"""Decode-step hot path: the sequence of ``vllm._C`` calls one engine step makes per decoder layer.
+
+This is the host-side mirror of the call order in the reference's model code, restricted to the
+ops in scope:
+
+    LlamaDecoderLayer.forward   vllm/model_executor/models/llama.py:215-238
+      input_layernorm           -> ops.rms_norm (first layer) / ops.fused_add_rms_norm
+      LlamaAttention.forward    llama.py:156-169
+        qkv_proj                   (cuBLAS GEMM - library code, not part of this path)
+        rotary_emb              -> ops.rotary_embedding          layers/rotary_embedding.py:143-161
+        Attention.forward       -> cache_ops.reshape_and_cache   attention/backends/flash_attn.py:192
+                                -> ops.paged_attention_v1|v2     attention/ops/paged_attn.py:83-161
+        o_proj                     (cuBLAS GEMM [+ all-reduce when TP>1])
+      post_attention_layernorm  -> ops.fused_add_rms_norm
+      LlamaMLP.forward          llama.py:75-79
+        gate_up_proj               (cuBLAS GEMM)
+        act_fn                  -> ops.silu_and_mul              layers/activation.py:31-36
+        down_proj                  (cuBLAS GEMM [+ all-reduce when TP>1])
+    LlamaModel.forward          llama.py:271-303: final norm -> ops.fused_add_rms_norm
+
+The GEMM outputs (qkv, o_proj, gate_up, down_proj) are stand-in buffers owned by the caller; the
+ops read and write them in place exactly as the reference layers do.  Everything goes through
+``vllm_ltr_b200._C`` (the drop-in ``vllm._C`` surface) - there is no other code path.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _C
+
+_PARTITION_SIZE = 512  # vllm/attention/ops/paged_attn.py:10
+
+
+@dataclass
+class ModelShape:
+    """Per-GPU shapes of one decoder layer (after tensor-parallel sharding)."""
+    name: str
+    hidden: int
+    layers: int
+    q_heads: int
+    kv_heads: int
+    head_size: int
+    inter: int
+    dtype: torch.dtype
+    kv_cache_dtype: str = "auto"
+    block_size: int = 16
+    rope_theta: float = 10000.0
+    max_pos: int = 8192
+    eps: float = 1e-5
+
+    def shard(self, tp: int) -> "ModelShape":
+        """Megatron column/row split used by the reference (llama.py:96-111): q heads and the
+        MLP width are divided, kv heads are divided or replicated."""
+        if tp == 1:
+            return self
+        assert self.q_heads % tp == 0 and self.inter % tp == 0
+        return ModelShape(f"{self.name}-tp{tp}", self.hidden, self.layers, self.q_heads // tp,
+                          max(1, self.kv_heads // tp), self.head_size, self.inter // tp,
+                          self.dtype, self.kv_cache_dtype, self.block_size, self.rope_theta,
+                          self.max_pos, self.eps)
+
+
+SHAPES = {
+    "llama-2-7b": ModelShape("llama-2-7b", 4096, 32, 32, 32, 128, 11008, torch.float16),
+    "llama-3-8b": ModelShape("llama-3-8b", 4096, 32, 32, 8, 128, 14336, torch.bfloat16,
+                             rope_theta=500000.0),
+    "llama-3-8b-fp8kv": ModelShape("llama-3-8b-fp8kv", 4096, 32, 32, 8, 128, 14336,
+                                   torch.bfloat16, "fp8", rope_theta=500000.0),
+    "llama-2-70b": ModelShape("llama-2-70b", 8192, 80, 64, 8, 128, 28672, torch.float16),
+}
+
+
+def cos_sin_cache(shape: ModelShape, device) -> torch.Tensor:
+    """RotaryEmbedding._compute_cos_sin_cache, layers/rotary_embedding.py:70-93."""
+    d = shape.head_size
+    inv_freq = 1.0 / (shape.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float) / d))
+    t = torch.arange(shape.max_pos, dtype=torch.float)
+    freqs = torch.einsum("i,j -> ij", t, inv_freq)
+    return torch.cat((freqs.cos(), freqs.sin()), dim=-1).to(shape.dtype).to(device)
+
+
+def forward_decode(query, key_cache, value_cache, block_tables, context_lens, max_context_len,
+                   kv_cache_dtype, num_kv_heads, scale, alibi_slopes, kv_scale, out=None,
+                   scratch=None, C=_C):
+    """PagedAttention.forward_decode (attention/ops/paged_attn.py:83-161), including the
+    reference's v1/v2 choice.  ``out`` / ``scratch`` let a caller reuse buffers across steps."""
+    output = torch.empty_like(query) if out is None else out
+    block_size = value_cache.shape[3]
+    num_seqs, num_heads, head_size = query.shape
+    parts = (max_context_len + _PARTITION_SIZE - 1) // _PARTITION_SIZE
+    use_v1 = max_context_len <= 8192 and (parts == 1 or num_seqs * num_heads > 512)
+    if use_v1:
+        C.ops.paged_attention_v1(output, query, key_cache, value_cache, num_kv_heads, scale,
+                                  block_tables, context_lens, block_size, max_context_len,
+                                  alibi_slopes, kv_cache_dtype, kv_scale)
+    else:
+        if scratch is None:
+            tmp = torch.empty(num_seqs, num_heads, parts, head_size, dtype=output.dtype,
+                              device=output.device)
+            es = torch.empty(num_seqs, num_heads, parts, dtype=torch.float32,
+                             device=output.device)
+            ml = torch.empty_like(es)
+        else:
+            tmp, es, ml = scratch
+        C.ops.paged_attention_v2(output, es, ml, tmp, query, key_cache, value_cache,
+                                  num_kv_heads, scale, block_tables, context_lens, block_size,
+                                  max_context_len, alibi_slopes, kv_cache_dtype, kv_scale)
+    return output
+
+
+class DecodeHotPath:
+    """State of one model replica's decode step: paged KV pool, norm weights, rope cache and the
+    stand-in GEMM output buffers; ``step()`` issues the per-layer op sequence."""
+
+    def __init__(self, shape: ModelShape, num_blocks: int, max_tokens: int, device, seed: int = 0,
+                 layers: Optional[int] = None, C=None):
+        # C: the extension module to drive.  Always vllm_ltr_b200._C in the product; bench.py's
+        # reference arm passes the reference's own CPU build of vllm._C (same surface) instead.
+        self.C = _C if C is None else C
+        self.shape = s = shape
+        self.device = device
+        self.layers = s.layers if layers is None else layers
+        self.num_blocks = num_blocks
+        g = torch.Generator(device=device).manual_seed(seed)
+        es = 1 if s.kv_cache_dtype == "fp8" else torch.tensor([], dtype=s.dtype).element_size()
+        self.x = 16 // es
+        cache_t = torch.uint8 if s.kv_cache_dtype == "fp8" else s.dtype
+        scale = s.head_size ** -0.5
+        # one [2, num_blocks, block_size*kv_heads*head_size] tensor per layer, re-viewed as the
+        # reference does (paged_attn.py:42-61)
+        self.kv_caches: List[torch.Tensor] = []
+        self.key_caches: List[torch.Tensor] = []
+        self.value_caches: List[torch.Tensor] = []
+        for _ in range(self.layers):
+            n = s.block_size * s.kv_heads * s.head_size
+            if s.kv_cache_dtype == "fp8":
+                kv = torch.randint(0, 0x38, (2, num_blocks, n), generator=g, device=device,
+                                   dtype=torch.uint8)          # finite e5m2 codes below 1.0
+            else:
+                kv = ((torch.rand(2, num_blocks, n, generator=g, device=device) * 2 - 1)
+                      * scale).to(cache_t)
+            self.kv_caches.append(kv)
+            self.key_caches.append(kv[0].view(num_blocks, s.kv_heads, s.head_size // self.x,
+                                              s.block_size, self.x))
+            self.value_caches.append(kv[1].view(num_blocks, s.kv_heads, s.head_size,
+                                                s.block_size))
+        self.norm_w = [(torch.randn(s.hidden, generator=g, device=device) * 0.1 + 1).to(s.dtype)
+                       for _ in range(2 * self.layers + 1)]
+        self.cos_sin = cos_sin_cache(s, device)
+        T = max_tokens
+        qkv_w = (s.q_heads + 2 * s.kv_heads) * s.head_size
+        rnd = lambda *sh: (torch.randn(*sh, generator=g, device=device) * 0.5).to(s.dtype)
+        # stand-ins for the cuBLAS GEMM outputs of one layer (reused by every layer)
+        self.qkv = rnd(T, qkv_w)
+        self.o_proj_out = rnd(T, s.hidden)
+        self.gate_up = rnd(T, 2 * s.inter)
+        self.down_out = rnd(T, s.hidden)
+        self.attn_out = torch.empty(T, s.q_heads * s.head_size, dtype=s.dtype, device=device)
+        self.act_out = torch.empty(T, s.inter, dtype=s.dtype, device=device)
+        self.hidden = rnd(T, s.hidden)
+        self.residual = torch.empty_like(self.hidden)
+        self.normed = torch.empty_like(self.hidden)
+        self.scale = float(scale)
+        self.attn_events = None   # optional [(start, end)] CUDA events around each attention call
+
+    def step(self, hidden_in: torch.Tensor, positions: torch.Tensor, slot_mapping: torch.Tensor,
+             block_tables: torch.Tensor, context_lens: torch.Tensor, max_context_len: int,
+             all_reduce=None) -> torch.Tensor:
+        """One decode step for ``T = hidden_in.shape[0]`` sequences (one new token each).
+        Returns the final-norm output [T, hidden] (what compute_logits consumes)."""
+        s = self.shape
+        ops, cache_ops = self.C.ops, self.C.cache_ops
+        T = hidden_in.shape[0]
+        qsz, kvsz = s.q_heads * s.head_size, s.kv_heads * s.head_size
+        qkv = self.qkv[:T]
+        q, k, v = qkv.split([qsz, kvsz, kvsz], dim=-1)
+        hidden = self.hidden[:T]
+        hidden.copy_(hidden_in)
+        residual = self.residual[:T]
+        attn_out = self.attn_out[:T]
+        for layer in range(self.layers):
+            # input_layernorm
+            if layer == 0:
+                residual.copy_(hidden)
+                ops.rms_norm(self.normed[:T], hidden, self.norm_w[0], s.eps)
+            else:
+                ops.fused_add_rms_norm(hidden, residual, self.norm_w[2 * layer], s.eps)
+            # [qkv_proj GEMM writes qkv]
+            ops.rotary_embedding(positions, q, k, s.head_size, self.cos_sin, True)
+            kc, vc = self.key_caches[layer], self.value_caches[layer]
+            cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
+                                        v.view(T, s.kv_heads, s.head_size), kc, vc, slot_mapping,
+                                        s.kv_cache_dtype, 1.0)
+            ev = self.attn_events
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            forward_decode(q.view(T, s.q_heads, s.head_size), kc, vc, block_tables, context_lens,
+                           max_context_len, s.kv_cache_dtype, s.kv_heads, self.scale, None, 1.0,
+                           out=attn_out.view(T, s.q_heads, s.head_size), C=self.C)
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
+            # [o_proj GEMM reads attn_out, writes o_proj_out; row-parallel => all-reduce]
+            hidden = self.o_proj_out[:T]
+            if all_reduce is not None:
+                all_reduce(hidden)
+            ops.fused_add_rms_norm(hidden, residual, self.norm_w[2 * layer + 1], s.eps)
+            # [gate_up_proj GEMM writes gate_up]
+            ops.silu_and_mul(self.act_out[:T], self.gate_up[:T])
+            # [down_proj GEMM reads act_out, writes down_out; row-parallel => all-reduce]
+            hidden = self.down_out[:T]
+            if all_reduce is not None:
+                all_reduce(hidden)
+        ops.fused_add_rms_norm(hidden, residual, self.norm_w[2 * self.layers], s.eps)
+        return hidden

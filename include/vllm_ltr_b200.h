@@ -123,6 +123,22 @@ int vltr_rotary_embedding(const int64_t* positions, void* query, void* key, int6
 int vltr_activation(void* out, const void* input, int64_t num_tokens, int d, int act, int dtype,
                     void* stream);
 
+/* ---- LTR scheduling tick: queue sort ---------------------------------------------------------
+ * Replaces `sorted(waiting + running + swapped, key=lambda r: (r.pri, -r.aux_model_score))`
+ * (vllm/core/scheduler.py:996; :998 without starvation control: pri == NULL) of
+ * Scheduler._get_opt_ordered_requests, bit-exactly: order[] = input positions by ascending
+ * (pri, negate ? -score : score), stable (ties keep input order), doubles compared like Python
+ * floats (-0.0 == +0.0).
+ * vltr_ltr_rank:      score/pri/order are DEVICE arrays of n entries; workspace is device memory
+ *                     of vltr_ltr_rank_workspace_bytes(n); asynchronous on `stream`.
+ * vltr_ltr_rank_host: score/pri/order are HOST arrays; stages through library-owned pinned
+ *                     buffers, runs the kernel and returns after the permutation is on the host. */
+size_t vltr_ltr_rank_workspace_bytes(int n);
+int vltr_ltr_rank(const double* score, const int32_t* pri, int n, int negate, int32_t* order,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int vltr_ltr_rank_host(const double* score, const int32_t* pri, int n, int negate, int32_t* order,
+                       void* stream);
+
 /* ---- cuda utils: csrc/cuda_utils_kernels.cu ---------------------------------------------- */
 int vltr_get_device_attribute(int attribute, int device_id);
 int vltr_get_max_shared_memory_per_block_device_attribute(int device_id);

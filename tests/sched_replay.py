@@ -1,0 +1,146 @@
+"""Replay harness for the LTR scheduling tick: drives a reference ``Scheduler`` (from
+/root/reference/vllm/core/scheduler.py) through a seeded request population and a simulated
+engine (the bookkeeping of LLMEngine._process_model_outputs, llm_engine.py:471-510, without a
+model), recording every tick's decision.  Used twice per scenario - once with the reference's own
+methods, once with vllm_ltr_b200.ltr_scheduler installed - and the two recordings must be
+identical."""
+import os
+import sys
+
+import numpy as np
+
+REF = "/root/reference"
+
+
+def have_reference() -> bool:
+    return os.path.isdir(os.path.join(REF, "vllm", "core"))
+
+
+def import_reference():
+    """Make `import vllm` resolve to the reference checkout (not the vllm wheel in the image)."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "vllm" or k.startswith("vllm.")]:
+        mod = sys.modules[k]
+        f = getattr(mod, "__file__", "") or ""
+        if not f.startswith(REF) and not k.startswith("vllm._C"):
+            del sys.modules[k]
+    import vllm  # noqa: F401
+    assert vllm.__file__.startswith(REF), vllm.__file__
+
+
+class StubScorer:
+    """scheduler.aux_model stand-in: fp16-quantised scores keyed by request id (many exact ties,
+    like `logits[:,0].tolist()` of the predictor, opt.py:399-409)."""
+
+    def __init__(self, scores):
+        self.scores = scores
+        self.calls = []
+
+    def obtain_aux_scores(self, seq_groups):
+        self.calls.append([g.request_id for g in seq_groups])
+        out = []
+        for g in seq_groups:
+            assert g.need_aux_model_score()
+            g.set_aux_model_score(self.scores[g.request_id])
+            out.append(self.scores[g.request_id])
+        return out
+
+
+class PythonRanker:
+    """Host-logic test double for the CUDA ranker: the reference's own expression."""
+
+    def order(self, scores, pri=None, negate=True):
+        n = len(scores)
+        sgn = -1.0 if negate else 1.0
+        if pri is None:
+            idx = sorted(range(n), key=lambda i: sgn * scores[i])
+        else:
+            idx = sorted(range(n), key=lambda i: (pri[i], sgn * scores[i]))
+        return np.asarray(idx, dtype=np.int32)
+
+
+def make_population(n, seed, max_prompt=96, max_out=48):
+    rng = np.random.default_rng(seed)
+    prompt = np.clip(np.rint(np.exp(rng.normal(3.0, 0.8, n))), 2, max_prompt).astype(int)
+    out = np.clip(np.rint(np.exp(rng.normal(2.5, 0.9, n))), 1, max_out).astype(int)
+    score = (-np.log(out) + rng.normal(0, 0.7, n)).astype(np.float16).astype(np.float64)
+    arrival = np.sort(rng.integers(0, max(1, n // 8), n))      # tick at which each arrives
+    return prompt, out, score, arrival
+
+
+def run(n, seed, schedule_type, num_gpu_blocks, num_cpu_blocks, block_size=4, max_tokens=64,
+        max_seqs=16, use_plugin=False, ranker=None, max_ticks=5000):
+    """Returns the list of per-tick records."""
+    import_reference()
+    from vllm import SamplingParams
+    from vllm.config import CacheConfig, SchedulerConfig
+    from vllm.core.scheduler import Scheduler
+    from vllm.sequence import Logprob, Sequence, SequenceGroup, SequenceStatus
+
+    prompt, out_len, score, arrival = make_population(n, seed)
+    sc = SchedulerConfig(max_tokens, max_seqs, 4096, enable_chunked_prefill=True,
+                         schedule_type=schedule_type)
+    cc = CacheConfig(block_size, 1.0, 1, "auto")
+    cc.num_gpu_blocks, cc.num_cpu_blocks = num_gpu_blocks, num_cpu_blocks
+    sched = Scheduler(sc, cc, None)
+    sched.aux_model = StubScorer({str(i): float(score[i]) for i in range(n)})
+    if use_plugin:
+        from vllm_ltr_b200 import ltr_scheduler
+        ltr_scheduler.install(sched, ranker=ranker)
+    groups = []
+    for i in range(n):
+        toks = list(range(int(prompt[i])))
+        seq = Sequence(i, " ".join(map(str, toks)), toks, block_size)
+        sp = SamplingParams(ignore_eos=True, max_tokens=int(out_len[i]))
+        groups.append(SequenceGroup(str(i), [seq], sp, 0.0))
+    records = []
+    nxt = 0
+    tick = 0
+    while tick < max_ticks:
+        while nxt < n and arrival[nxt] <= tick:
+            sched.add_seq_group(groups[nxt])
+            nxt += 1
+        if not sched.has_unfinished_seqs():
+            if nxt >= n:
+                break
+            tick += 1
+            continue
+        metas, outs = sched.schedule()
+        rec = {
+            "sched": [(s.seq_group.request_id, s.token_chunk_size, m.is_prompt)
+                      for s, m in zip(outs.scheduled_seq_groups, metas)],
+            # physical block NUMBERS are not reproducible even between two runs of the reference:
+            # BlockSpaceManagerV1.free iterates `set(block_table)` (block_manager_v1.py:560-564),
+            # i.e. in object-address order, so the free list is permuted run to run.  Sizes are.
+            "block_tables": [sorted((k, len(v)) for k, v in m.block_tables.items())
+                             for m in metas],
+            "n_prefill": outs.num_prefill_groups,
+            "n_tokens": outs.num_batched_tokens,
+            "swap_in": len(outs.blocks_to_swap_in),
+            "swap_out": len(outs.blocks_to_swap_out),
+            "copy": sorted(len(v) for v in outs.blocks_to_copy.values()),
+            "free_gpu": sched.block_manager.get_num_free_gpu_blocks(),
+            "free_cpu": sched.block_manager.get_num_free_cpu_blocks(),
+            "waiting": [g.request_id for g in sched.waiting],
+            "running": [g.request_id for g in sched.running],
+            "swapped": [g.request_id for g in sched.swapped],
+            "state": [(g.request_id, g.idle, g.runs, g.pri, g.running_info["swap_out"],
+                       g.running_info["swap_blocks"], hasattr(g, "num_new_tokens"))
+                      for g in list(sched.swapped) + list(sched.running) + list(sched.waiting)],
+        }
+        records.append(rec)
+        # simulated engine step (llm_engine.py:489-499): computed-token bookkeeping, one sampled
+        # token for every group whose prompt is fully computed, stop at max_tokens
+        for s in outs.scheduled_seq_groups:
+            g = s.seq_group
+            g.update_num_computed_tokens(s.token_chunk_size)
+            if g.get_num_uncomputed_tokens() == 0:
+                for seq in g.get_seqs(status=SequenceStatus.RUNNING):
+                    seq.append_token_id(7, {7: Logprob(0.0)})
+                    if seq.get_output_len() >= g.sampling_params.max_tokens:
+                        seq.status = SequenceStatus.FINISHED_LENGTH_CAPPED
+                        sched.free_seq(seq)
+        sched.free_finished_seq_groups()
+        tick += 1
+    return records

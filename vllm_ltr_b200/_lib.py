@@ -38,6 +38,9 @@ _SIGS = {
     "vltr_rotary_embedding": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int64,
                                       c_int64, _P, _P, c_int, c_int, _P]),
     "vltr_activation": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "vltr_ltr_rank_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "vltr_ltr_rank": (c_int, [_P, _P, c_int, c_int, _P, _P, ctypes.c_size_t, _P]),
+    "vltr_ltr_rank_host": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "vltr_get_device_attribute": (c_int, [c_int, c_int]),
     "vltr_get_max_shared_memory_per_block_device_attribute": (c_int, [c_int]),
 }

@@ -108,7 +108,7 @@ def test_tick_cost_is_linear():
     for plugin in (False, True):
         s = build(plugin)
         ticks, outs = [], []
-        for _ in range(4):
+        for _ in range(24):     # reach the steady state: a full running queue
             t0 = time.perf_counter()
             metas, o = s.schedule()
             ticks.append(time.perf_counter() - t0)
@@ -118,7 +118,7 @@ def test_tick_cost_is_linear():
                 if x.seq_group.get_num_uncomputed_tokens() == 0:
                     for seq in x.seq_group.get_seqs(status=SequenceStatus.RUNNING):
                         seq.append_token_id(7, {7: Logprob(0.0)})
-        res[plugin] = (min(ticks[1:]), outs)
+        res[plugin] = (min(ticks[-5:]), outs)
     assert res[False][1] == res[True][1]
     print(f"tick @10k live: reference {res[False][0]*1e3:.1f} ms, plugin {res[True][0]*1e3:.1f} ms")
     assert res[True][0] < res[False][0] / 2

@@ -139,6 +139,57 @@ int vltr_ltr_rank(const double* score, const int32_t* pri, int n, int negate, in
 int vltr_ltr_rank_host(const double* score, const int32_t* pri, int n, int negate, int32_t* order,
                        void* stream);
 
+/* ---- LTR scheduling tick: predictor forward ---------------------------------------------------
+ * Replaces the GPU work of AUXLLMEngine.obtain_aux_scores (vllm/engine/aux_llm_engine.py:332-412):
+ * OPTForSequenceClassification.forward + compute_logits (vllm/model_executor/models/opt.py:362-397)
+ * on a batch of prompts, prefill only, no KV cache.  All pointers are DEVICE pointers owned by the
+ * caller; weights are row-major [out, in] (torch nn.Linear / HF checkpoint layout), dtype f16 or
+ * bf16; qkv_w/qkv_b are the q,k,v projections stacked along `out` (3*hidden).
+ *   token_ids  [num_tokens] int32    prompts concatenated
+ *   positions  [num_tokens] int32    0-based position of each token inside its prompt
+ *   cu_seqlens [num_prompts+1] int32 prefix sums of prompt lengths
+ *   last_rows  [num_prompts] int32   index of each prompt's last token (cu_seqlens[i+1]-1)
+ *   logits     [num_prompts, num_labels] float, each value rounded to the model dtype first (the
+ *              reference's logits tensor is f16; scores are logits[:,0].tolist(), opt.py:399-409)
+ * Asynchronous on `stream`; workspace of vltr_opt_workspace_bytes(handle, tokens, prompts) bytes,
+ * 256-byte aligned. */
+#define VLTR_OPT_MAX_LAYERS 48
+typedef struct vltr_opt_config {
+  int hidden, layers, heads, ffn, vocab, max_pos; /* max_pos = max_position_embeddings          */
+  int embed_dim;                                  /* word_embed_proj_dim (== hidden for 125M)    */
+  int num_labels;
+  int do_layer_norm_before;                       /* 1: OPT-125M style pre-LN, 0: OPT-350M post-LN */
+  int final_layer_norm;                           /* decoder.final_layer_norm present             */
+  int dtype;                                      /* VLTR_F16 / VLTR_BF16                         */
+} vltr_opt_config;
+typedef struct vltr_opt_weights {
+  const void* embed_tokens;    /* [vocab, embed_dim]     */
+  const void* embed_positions; /* [max_pos + 2, hidden]  */
+  const void* project_in;      /* [hidden, embed_dim] or NULL */
+  const void* project_out;     /* [embed_dim, hidden] or NULL */
+  const void* final_ln_w;
+  const void* final_ln_b;
+  const void* score;           /* [num_labels, embed_dim] */
+  const void* ln1_w[VLTR_OPT_MAX_LAYERS];  const void* ln1_b[VLTR_OPT_MAX_LAYERS];
+  const void* qkv_w[VLTR_OPT_MAX_LAYERS];  const void* qkv_b[VLTR_OPT_MAX_LAYERS];
+  const void* out_w[VLTR_OPT_MAX_LAYERS];  const void* out_b[VLTR_OPT_MAX_LAYERS];
+  const void* ln2_w[VLTR_OPT_MAX_LAYERS];  const void* ln2_b[VLTR_OPT_MAX_LAYERS];
+  const void* fc1_w[VLTR_OPT_MAX_LAYERS];  const void* fc1_b[VLTR_OPT_MAX_LAYERS];
+  const void* fc2_w[VLTR_OPT_MAX_LAYERS];  const void* fc2_b[VLTR_OPT_MAX_LAYERS];
+} vltr_opt_weights;
+int vltr_opt_create(const vltr_opt_config* cfg, const vltr_opt_weights* weights, void** handle);
+void vltr_opt_destroy(void* handle);
+size_t vltr_opt_workspace_bytes(const void* handle, int max_tokens, int max_prompts);
+int vltr_opt_forward(const void* handle, const int32_t* token_ids, const int32_t* positions,
+                     const int32_t* cu_seqlens, const int32_t* last_rows, int num_tokens,
+                     int num_prompts, int max_len, void* workspace, size_t workspace_bytes,
+                     float* logits, void* stream);
+/* The dense layer the predictor is built from, exposed for tests:
+ * D[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + resid[M,N]  (tcgen05.mma, fp32 accumulate in TMEM;
+ * bias / resid may be NULL; N % 64 == 0, K % 8 == 0; dtype f16 / bf16). */
+int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias, const void* resid, int M,
+                  int N, int K, int relu, int dtype, void* stream);
+
 /* ---- cuda utils: csrc/cuda_utils_kernels.cu ---------------------------------------------- */
 int vltr_get_device_attribute(int attribute, int device_id);
 int vltr_get_max_shared_memory_per_block_device_attribute(int device_id);

@@ -1,0 +1,677 @@
+// opt_predictor.cu — forward pass of the learning-to-rank predictor (OPT-125M / OPT-350M
+// sequence classifier), prefill only, no KV cache.
+//
+// Replaces what AUXLLMEngine.obtain_aux_scores (vllm/engine/aux_llm_engine.py:332-412) runs on
+// the GPU through a whole second engine: OPTForSequenceClassification.forward + compute_logits
+// (vllm/model_executor/models/opt.py:362-409; decoder :181-310, layer :101-178, attention :57-98,
+// flash_attn_varlen prefill path attention/backends/flash_attn.py:217-235).
+//
+// Op order and rounding points follow the reference (every op writes T = fp16/bf16 activations,
+// fp32 accumulation inside):
+//   h = embed_tokens[id] (-> project_in) + embed_positions[pos + 2]
+//   per layer (pre-LN, OPT-125M):  h += out_proj(attn(qkv_proj(LN1(h))));  h += fc2(relu(fc1(LN2(h))))
+//   per layer (post-LN, OPT-350M): h = LN1(h + out_proj(attn(qkv_proj(h))));  h = LN2(h + fc2(relu(fc1(h))))
+//   last token of every prompt -> final LN -> (project_out) -> logits = x . score.weight^T
+//
+// B200 shape
+//   * the dense layers (the only contraction in scope) run on the 5th-generation tensor cores:
+//     one tcgen05.mma stream per CTA issued by a single thread, A/B tiles staged in shared memory
+//     by TMA (128-byte swizzle) through a 4-stage mbarrier ring, fp32 accumulators in TMEM, and a
+//     tcgen05.ld epilogue that fuses bias, ReLU and the residual add before the one global store;
+//   * LayerNorm is one warp per token row, attention is a causal varlen kernel with one thread
+//     per query row (online softmax in registers, K/V tiles broadcast from shared memory) - the
+//     predictor sees a few hundred tokens per tick, these are latency-, not throughput-, critical;
+//   * the whole forward is ~8 launches per layer on one stream with no host synchronisation; the
+//     caller reads the [num_prompts, num_labels] logits back once.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace vltr {
+namespace opt {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128 x N x 16 step
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense layer on tcgen05:  D[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + resid[M,N]
+// ------------------------------------------------------------------------------------------------
+constexpr int kBM = 128;      // UMMA M (one TMEM lane per output row)
+constexpr int kBK = 64;       // 64 halfs = 128 bytes = one swizzle row
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 128;
+
+template <int BN>
+__host__ __device__ constexpr int gemm_smem_bytes() {
+  return kStages * (kBM * kBK * 2 + BN * kBK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+// K-major, 128-byte swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout SWIZZLE_128B = 2 [61,64))
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) [4,6), a/b format [7,10)/[10,13)
+// (0 = f16, 1 = bf16), both K-major, N>>3 [17,23), M>>4 [24,29)
+template <typename T, int BN>
+__device__ __forceinline__ uint32_t make_idesc() {
+  const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(kBM >> 4) << 24);
+}
+
+template <typename T, int BN, bool RELU>
+__global__ void __launch_bounds__(kGemmThreads)
+    gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a,
+                   const __grid_constant__ CUtensorMap map_b, T* __restrict__ D,
+                   const T* __restrict__ bias, const T* __restrict__ resid, int M, int N, int K) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2;
+  constexpr uint32_t STAGE = A_BYTES + B_BYTES;
+  const uint32_t bars = base + kStages * STAGE;       // full[kStages], empty[kStages], tmem_full
+  const uint32_t full0 = bars, empty0 = bars + 8 * kStages, tfull = bars + 16 * kStages;
+  const uint32_t slot = tfull + 8;
+  volatile uint32_t* slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int nk = (K + kBK - 1) / kBK;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(slot, BN);   // BN fp32 accumulator columns (power of two >= 32)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer ---------------------------------------------------------------------------
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      mbar_expect_tx(full0 + 8 * s, STAGE);
+      tma_load_2d(base + s * STAGE, &map_a, kb * kBK, m0, full0 + 8 * s);
+      tma_load_2d(base + s * STAGE + A_BYTES, &map_b, kb * kBK, n0, full0 + 8 * s);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer -----------------------------------------------------------------------------
+    const uint32_t idesc = make_idesc<T, BN>();
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      const uint64_t ad = make_desc_sw128(base + s * STAGE);
+      const uint64_t bd = make_desc_sw128(base + s * STAGE + A_BYTES);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (2 x 16 B) per K = 16 step inside the atom
+        umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+      umma_commit(empty0 + 8 * s);          // frees the stage when these MMAs have read it
+    }
+    umma_commit(tfull);                      // accumulator complete
+  }
+
+  // ---- epilogue: TMEM -> registers -> bias / relu / residual -> global ---------------------------
+  mbar_wait(tfull, 0);
+  __syncwarp();
+  tc_fence_after();
+  const int row = m0 + warp * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(trow + c * 32, r);
+    const int col = n0 + c * 32;
+    if (row < M) {
+      T* drow = D + (int64_t)row * N + col;
+      const T* rrow = resid != nullptr ? resid + (int64_t)row * N + col : nullptr;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {          // 4 x 16-byte stores of 8 elements
+        alignas(16) T o[8];
+        alignas(16) T rs[8];
+        alignas(16) T bs[8];
+        if (rrow != nullptr) *reinterpret_cast<uint4*>(rs) = *reinterpret_cast<const uint4*>(rrow + v * 8);
+        if (bias != nullptr) *reinterpret_cast<uint4*>(bs) = __ldg(reinterpret_cast<const uint4*>(bias + col + v * 8));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float x = __uint_as_float(r[v * 8 + e]);
+          if (bias != nullptr) x += ST<T>::to_f(bs[e]);
+          if (RELU) x = fmaxf(x, 0.f);
+          if (rrow != nullptr) x = rt<T>(x) + ST<T>::to_f(rs[e]);   // linear output is T, then + residual
+          o[e] = ST<T>::from_f(x);
+        }
+        st_16(drow + v * 8, *reinterpret_cast<uint4*>(o));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+// out[t, :] = tok[ids[t], :E] (+ pos[positions[t] + 2, :] when ADD_POS; requires E == H then)
+template <typename T>
+__global__ void __launch_bounds__(128)
+    embed_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ positions,
+                 const T* __restrict__ tok, const T* __restrict__ pos, T* __restrict__ out, int E,
+                 int add_pos) {
+  const int t = blockIdx.x;
+  const T* src = tok + (int64_t)ids[t] * E;
+  const T* p = pos + ((int64_t)positions[t] + 2) * E;   // OPTLearnedPositionalEmbedding offset 2
+  for (int i = threadIdx.x * 8; i < E; i += blockDim.x * 8) {
+    alignas(16) T a[8];
+    *reinterpret_cast<uint4*>(a) = *reinterpret_cast<const uint4*>(src + i);
+    if (add_pos) {
+      alignas(16) T b[8];
+      *reinterpret_cast<uint4*>(b) = *reinterpret_cast<const uint4*>(p + i);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = ST<T>::from_f(ST<T>::to_f(a[e]) + ST<T>::to_f(b[e]));
+    }
+    *reinterpret_cast<uint4*>(out + (int64_t)t * E + i) = *reinterpret_cast<uint4*>(a);
+  }
+}
+
+// h[t, :] += pos[positions[t] + 2, :]   (after project_in, OPT-350M)
+template <typename T>
+__global__ void __launch_bounds__(128)
+    add_pos_kernel(const int32_t* __restrict__ positions, const T* __restrict__ pos,
+                   T* __restrict__ h, int H) {
+  const int t = blockIdx.x;
+  const T* p = pos + ((int64_t)positions[t] + 2) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    h[(int64_t)t * H + i] = ST<T>::from_f(ST<T>::to_f(h[(int64_t)t * H + i]) + ST<T>::to_f(p[i]));
+}
+
+// LayerNorm, one warp per row.  rows == nullptr: row r of `in` -> row r of `out`;
+// else row rows[r] of `in` -> row r of `out` (gather of the last token of every prompt).
+template <typename T>
+__global__ void __launch_bounds__(128)
+    layernorm_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ w,
+                     const T* __restrict__ b, const int32_t* __restrict__ rows, int nrows, int H,
+                     float eps, int identity) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const T* x = in + (int64_t)(rows != nullptr ? rows[r] : r) * H;
+  T* y = out + (int64_t)r * H;
+  if (identity) {   // no final layer norm: plain gather
+    for (int i = lane; i < H; i += 32) y[i] = x[i];
+    return;
+  }
+  float s = 0.f;
+  for (int i = lane; i < H; i += 32) s += ST<T>::to_f(x[i]);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  const float mean = s / H;
+  float v = 0.f;
+  for (int i = lane; i < H; i += 32) {
+    const float d = ST<T>::to_f(x[i]) - mean;
+    v += d * d;
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  const float rstd = rsqrtf(v / H + eps);
+  for (int i = lane; i < H; i += 32)
+    y[i] = ST<T>::from_f((ST<T>::to_f(x[i]) - mean) * rstd * ST<T>::to_f(w[i]) + ST<T>::to_f(b[i]));
+}
+
+// causal varlen attention, head size 64.  qkv [M, 3H] (q | k | v), out [M, H].
+// grid (q tiles of 128 rows over max_len, heads, prompts); one thread per query row.
+__device__ __forceinline__ float fma_mixed(__half a, __half b, float c) {
+  float r;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fma_mixed(__nv_bfloat16 a, __nv_bfloat16 b, float c) {
+  float r;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;"
+      : "=f"(r)
+      : "h"(__bfloat16_as_ushort(a)), "h"(__bfloat16_as_ushort(b)), "f"(c));
+  return r;
+}
+
+constexpr int kAttnRows = 128, kAttnKeys = 64, kHD = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnRows)
+    attention_kernel(const T* __restrict__ qkv, T* __restrict__ out,
+                     const int32_t* __restrict__ cu_seqlens, int H, float scale) {
+  __shared__ __align__(16) T sk[kAttnKeys][kHD];
+  __shared__ __align__(16) T sv[kAttnKeys][kHD];
+  const int prompt = blockIdx.z, head = blockIdx.y;
+  const int t0 = cu_seqlens[prompt], len = cu_seqlens[prompt + 1] - t0;
+  const int q0 = blockIdx.x * kAttnRows;
+  if (q0 >= len) return;
+  const int qi = q0 + threadIdx.x;            // my query position inside the prompt
+  const bool live = qi < len;
+  const int64_t ld = 3 * (int64_t)H;
+  alignas(16) T q[kHD];
+  if (live) {
+    const T* qp = qkv + (t0 + qi) * ld + head * kHD;
+#pragma unroll
+    for (int i = 0; i < kHD; i += 8)
+      *reinterpret_cast<uint4*>(&q[i]) = *reinterpret_cast<const uint4*>(qp + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) q[i] = ST<T>::from_f(0.f);
+  }
+  float o[kHD];
+#pragma unroll
+  for (int i = 0; i < kHD; ++i) o[i] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const float sl2 = scale * 1.4426950408889634f;
+  const int kmax = min(len, q0 + kAttnRows);   // causal: keys up to the last query of this tile
+  for (int k0 = 0; k0 < kmax; k0 += kAttnKeys) {
+    __syncthreads();
+    // stage K and V rows k0 .. k0+63 of this head (64 rows x 128 B each)
+    for (int i = threadIdx.x; i < kAttnKeys * (kHD / 8); i += kAttnRows) {
+      const int r = i / (kHD / 8), c = (i % (kHD / 8)) * 8;
+      uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (k0 + r < len) {
+        const T* kp = qkv + (t0 + k0 + r) * ld + H + head * kHD + c;
+        kk = *reinterpret_cast<const uint4*>(kp);
+        vv = *reinterpret_cast<const uint4*>(kp + H);
+      }
+      *reinterpret_cast<uint4*>(&sk[r][c]) = kk;
+      *reinterpret_cast<uint4*>(&sv[r][c]) = vv;
+    }
+    __syncthreads();
+    const int nkeys = min(kAttnKeys, kmax - k0);
+    for (int j = 0; j < nkeys; ++j) {
+      if (k0 + j > qi) break;                  // causal mask (also retires rows past the prompt)
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < kHD; i += 8) {
+        alignas(16) T kk[8];
+        *reinterpret_cast<uint4*>(kk) = *reinterpret_cast<const uint4*>(&sk[j][i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s = fma_mixed(q[i + e], kk[e], s);
+      }
+      s *= sl2;
+      const float mn = fmaxf(m, s);
+      if (mn > m) {
+        const float a = exp2f(m - mn);
+        l *= a;
+#pragma unroll
+        for (int i = 0; i < kHD; ++i) o[i] *= a;
+        m = mn;
+      }
+      const T ph = ST<T>::from_f(exp2f(s - m));   // P is rounded to T before P.V, as flash-attn does
+      l += ST<T>::to_f(ph);
+#pragma unroll
+      for (int i = 0; i < kHD; i += 8) {
+        alignas(16) T vv[8];
+        *reinterpret_cast<uint4*>(vv) = *reinterpret_cast<const uint4*>(&sv[j][i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[i + e] = fma_mixed(ph, vv[e], o[i + e]);
+      }
+    }
+  }
+  if (live) {
+    const float inv = 1.f / l;
+    T* op = out + (int64_t)(t0 + qi) * H + head * kHD;
+#pragma unroll
+    for (int i = 0; i < kHD; i += 8) {
+      alignas(16) T r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = ST<T>::from_f(o[i + e] * inv);
+      *reinterpret_cast<uint4*>(op + i) = *reinterpret_cast<uint4*>(r);
+    }
+  }
+}
+
+// logits[i, l] = (T)(x[i, :] . w[l, :]) as float;  one warp per (prompt, label)
+template <typename T>
+__global__ void __launch_bounds__(128)
+    score_kernel(const T* __restrict__ x, const T* __restrict__ w, float* __restrict__ logits,
+                 int n, int labels, int E) {
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (idx >= n * labels) return;
+  const int i = idx / labels, lbl = idx % labels;
+  float s = 0.f;
+  for (int e = lane; e < E; e += 32)
+    s += ST<T>::to_f(x[(int64_t)i * E + e]) * ST<T>::to_f(w[(int64_t)lbl * E + e]);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) logits[idx] = rt<T>(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// 2-D map over a row-major [rows, cols] 16-bit matrix, box = [box_rows, 64 cols], 128 B swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int box_rows, int dtype) {
+  EncodeTiledFn fn = encode_fn();
+  VLTR_CHECK(fn != nullptr, VLTR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, dtype == VLTR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                        2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VLTR_CHECK(r == CUDA_SUCCESS, VLTR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VLTR_OK;
+}
+
+template <typename T, int BN, bool RELU>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const void* bias,
+                       const void* resid, int M, int N, int K, cudaStream_t stream) {
+  auto kern = gemm_tn_kernel<T, BN, RELU>;
+  static bool configured = false;
+  if (!configured) {
+    VLTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   gemm_smem_bytes<BN>()));
+    configured = true;
+  }
+  dim3 grid(N / BN, (M + kBM - 1) / kBM);
+  kern<<<grid, kGemmThreads, gemm_smem_bytes<BN>(), stream>>>(ma, mb, (T*)D, (const T*)bias,
+                                                            (const T*)resid, M, N, K);
+  VLTR_LAUNCH_CHECK("opt_gemm");
+  return VLTR_OK;
+}
+
+// D = act(A . W^T + bias) + resid;  A [M,K], W [N,K], all row-major T
+static int gemm(const void* A, const void* W, void* D, const void* bias, const void* resid,
+                int M, int N, int K, int relu, int dtype, cudaStream_t stream) {
+  VLTR_CHECK(M > 0 && N > 0 && K > 0, VLTR_ERR_INVALID, "opt_gemm: empty problem");
+  VLTR_CHECK(N % 64 == 0 && K % 8 == 0, VLTR_ERR_UNSUPPORTED,
+             "opt_gemm: N %d must be a multiple of 64 and K %d of 8", N, K);
+  VLTR_CHECK(((uintptr_t)A | (uintptr_t)W | (uintptr_t)D | (uintptr_t)bias | (uintptr_t)resid) % 16 == 0,
+             VLTR_ERR_INVALID, "opt_gemm: operands must be 16-byte aligned");
+  // wide tiles when they still give every SM a CTA, else narrow ones
+  const int tiles128 = (N / 128) * ((M + kBM - 1) / kBM);
+  const bool wide = N % 128 == 0 && tiles128 >= num_sms();
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, K, kBM, dtype);
+  if (rc) return rc;
+  rc = make_map(&mb, W, N, K, wide ? 128 : 64, dtype);
+  if (rc) return rc;
+#define VLTR_GEMM(TT)                                                                            \
+  if (wide)                                                                                      \
+    return relu ? launch_gemm<TT, 128, true>(ma, mb, D, bias, resid, M, N, K, stream)            \
+                : launch_gemm<TT, 128, false>(ma, mb, D, bias, resid, M, N, K, stream);          \
+  return relu ? launch_gemm<TT, 64, true>(ma, mb, D, bias, resid, M, N, K, stream)               \
+              : launch_gemm<TT, 64, false>(ma, mb, D, bias, resid, M, N, K, stream);
+  if (dtype == VLTR_F16) {
+    VLTR_GEMM(__half)
+  } else if (dtype == VLTR_BF16) {
+    VLTR_GEMM(__nv_bfloat16)
+  }
+#undef VLTR_GEMM
+  return fail(VLTR_ERR_UNSUPPORTED, "opt_gemm: dtype %d (f16 / bf16 only)", dtype);
+}
+
+struct Model {
+  vltr_opt_config cfg;
+  vltr_opt_weights w;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <typename T>
+static int forward_t(const Model& mdl, const int32_t* ids, const int32_t* positions,
+                     const int32_t* cu_seqlens, const int32_t* last_rows, int M, int P, int max_len,
+                     char* ws, float* logits, cudaStream_t s) {
+  const vltr_opt_config& c = mdl.cfg;
+  const vltr_opt_weights& w = mdl.w;
+  const int H = c.hidden, E = c.embed_dim, F = c.ffn, dt = c.dtype;
+  const size_t es = sizeof(T);
+  // workspace carve-up
+  T* h = (T*)ws;            ws += align256((size_t)M * H * es);
+  T* x = (T*)ws;            ws += align256((size_t)M * H * es);
+  T* qkv = (T*)ws;          ws += align256((size_t)M * 3 * H * es);
+  T* att = (T*)ws;          ws += align256((size_t)M * H * es);
+  T* ff = (T*)ws;           ws += align256((size_t)M * F * es);
+  T* emb = (T*)ws;          ws += align256((size_t)M * E * es);
+  T* last = (T*)ws;         ws += align256((size_t)P * H * es);
+  T* last_e = (T*)ws;       ws += align256((size_t)P * E * es);
+  int rc;
+  const float scale = 1.0f / sqrtf((float)(H / c.heads));
+
+  if (E == H) {
+    embed_kernel<T><<<M, 128, 0, s>>>(ids, positions, (const T*)w.embed_tokens,
+                                      (const T*)w.embed_positions, h, E, 1);
+    VLTR_LAUNCH_CHECK("opt_embed");
+  } else {
+    embed_kernel<T><<<M, 128, 0, s>>>(ids, positions, (const T*)w.embed_tokens,
+                                      (const T*)w.embed_positions, emb, E, 0);
+    VLTR_LAUNCH_CHECK("opt_embed");
+    if ((rc = gemm(emb, w.project_in, h, nullptr, nullptr, M, H, E, 0, dt, s))) return rc;
+    add_pos_kernel<T><<<M, 128, 0, s>>>(positions, (const T*)w.embed_positions, h, H);
+    VLTR_LAUNCH_CHECK("opt_add_pos");
+  }
+  const int ln_grid = (M + 3) / 4;
+  const dim3 agrid((max_len + kAttnRows - 1) / kAttnRows, c.heads, P);
+  for (int L = 0; L < c.layers; ++L) {
+    const T* a_in = h;
+    if (c.do_layer_norm_before) {
+      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(h, x, (const T*)w.ln1_w[L], (const T*)w.ln1_b[L],
+                                                  nullptr, M, H, 1e-5f, 0);
+      VLTR_LAUNCH_CHECK("opt_layernorm");
+      a_in = x;
+    }
+    if ((rc = gemm(a_in, w.qkv_w[L], qkv, w.qkv_b[L], nullptr, M, 3 * H, H, 0, dt, s))) return rc;
+    attention_kernel<T><<<agrid, kAttnRows, 0, s>>>(qkv, att, cu_seqlens, H, scale);
+    VLTR_LAUNCH_CHECK("opt_attention");
+    if (c.do_layer_norm_before) {
+      // h = h + out_proj(att)
+      if ((rc = gemm(att, w.out_w[L], h, w.out_b[L], h, M, H, H, 0, dt, s))) return rc;
+      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(h, x, (const T*)w.ln2_w[L], (const T*)w.ln2_b[L],
+                                                  nullptr, M, H, 1e-5f, 0);
+      VLTR_LAUNCH_CHECK("opt_layernorm");
+      if ((rc = gemm(x, w.fc1_w[L], ff, w.fc1_b[L], nullptr, M, F, H, 1, dt, s))) return rc;
+      if ((rc = gemm(ff, w.fc2_w[L], h, w.fc2_b[L], h, M, H, F, 0, dt, s))) return rc;
+    } else {
+      // h = LN1(h + out_proj(att)); h = LN2(h + fc2(relu(fc1(h))))
+      if ((rc = gemm(att, w.out_w[L], x, w.out_b[L], h, M, H, H, 0, dt, s))) return rc;
+      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(x, h, (const T*)w.ln1_w[L], (const T*)w.ln1_b[L],
+                                                  nullptr, M, H, 1e-5f, 0);
+      VLTR_LAUNCH_CHECK("opt_layernorm");
+      if ((rc = gemm(h, w.fc1_w[L], ff, w.fc1_b[L], nullptr, M, F, H, 1, dt, s))) return rc;
+      if ((rc = gemm(ff, w.fc2_w[L], x, w.fc2_b[L], h, M, H, F, 0, dt, s))) return rc;
+      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(x, h, (const T*)w.ln2_w[L], (const T*)w.ln2_b[L],
+                                                  nullptr, M, H, 1e-5f, 0);
+      VLTR_LAUNCH_CHECK("opt_layernorm");
+    }
+  }
+  // last token of every prompt -> final LN (row-wise, so only those rows are normalised)
+  layernorm_kernel<T><<<(P + 3) / 4, 128, 0, s>>>(h, last, (const T*)w.final_ln_w,
+                                                  (const T*)w.final_ln_b, last_rows, P, H, 1e-5f,
+                                                  c.final_layer_norm ? 0 : 1);
+  VLTR_LAUNCH_CHECK("opt_final_layernorm");
+  const T* feat = last;
+  if (E != H) {
+    if ((rc = gemm(last, w.project_out, last_e, nullptr, nullptr, P, E, H, 0, dt, s))) return rc;
+    feat = last_e;
+  }
+  score_kernel<T><<<(P * c.num_labels + 3) / 4, 128, 0, s>>>(feat, (const T*)w.score, logits, P,
+                                                             c.num_labels, E);
+  VLTR_LAUNCH_CHECK("opt_score");
+  return VLTR_OK;
+}
+
+}  // namespace opt
+}  // namespace vltr
+
+extern "C" int vltr_opt_create(const vltr_opt_config* cfg, const vltr_opt_weights* weights,
+                               void** handle) {
+  using namespace vltr;
+  VLTR_CHECK(cfg != nullptr && weights != nullptr && handle != nullptr, VLTR_ERR_INVALID,
+             "opt_create: null argument");
+  VLTR_CHECK(cfg->layers > 0 && cfg->layers <= VLTR_OPT_MAX_LAYERS, VLTR_ERR_UNSUPPORTED,
+             "opt_create: %d layers (max %d)", cfg->layers, VLTR_OPT_MAX_LAYERS);
+  VLTR_CHECK(cfg->heads > 0 && cfg->hidden == cfg->heads * 64, VLTR_ERR_UNSUPPORTED,
+             "opt_create: head size must be 64 (hidden %d, heads %d)", cfg->hidden, cfg->heads);
+  VLTR_CHECK(cfg->hidden % 64 == 0 && cfg->ffn % 64 == 0 && cfg->embed_dim % 64 == 0,
+             VLTR_ERR_UNSUPPORTED, "opt_create: hidden / ffn / embed_dim must be multiples of 64");
+  VLTR_CHECK(cfg->dtype == VLTR_F16 || cfg->dtype == VLTR_BF16, VLTR_ERR_UNSUPPORTED,
+             "opt_create: dtype %d (f16 / bf16 only)", cfg->dtype);
+  VLTR_CHECK(cfg->num_labels >= 1, VLTR_ERR_INVALID, "opt_create: num_labels %d", cfg->num_labels);
+  opt::Model* m = new opt::Model{*cfg, *weights};
+  *handle = m;
+  return VLTR_OK;
+}
+
+extern "C" void vltr_opt_destroy(void* handle) { delete reinterpret_cast<vltr::opt::Model*>(handle); }
+
+extern "C" size_t vltr_opt_workspace_bytes(const void* handle, int max_tokens, int max_prompts) {
+  using namespace vltr::opt;
+  const Model* m = reinterpret_cast<const Model*>(handle);
+  const vltr_opt_config& c = m->cfg;
+  const size_t es = 2, M = max_tokens, P = max_prompts;
+  return align256(M * c.hidden * es) * 3 + align256(M * 3 * c.hidden * es) +
+         align256(M * c.ffn * es) + align256(M * c.embed_dim * es) + align256(P * c.hidden * es) +
+         align256(P * c.embed_dim * es) + 1024;
+}
+
+extern "C" int vltr_opt_forward(const void* handle, const int32_t* token_ids,
+                                const int32_t* positions, const int32_t* cu_seqlens,
+                                const int32_t* last_rows, int num_tokens, int num_prompts,
+                                int max_len, void* workspace, size_t workspace_bytes,
+                                float* logits, void* stream) {
+  using namespace vltr;
+  VLTR_CHECK(handle != nullptr, VLTR_ERR_INVALID, "opt_forward: null handle");
+  const opt::Model* m = reinterpret_cast<const opt::Model*>(handle);
+  VLTR_CHECK(num_tokens >= 0 && num_prompts >= 0 && max_len >= 0, VLTR_ERR_INVALID,
+             "opt_forward: negative size");
+  if (num_tokens == 0 || num_prompts == 0) return VLTR_OK;
+  VLTR_CHECK(max_len <= m->cfg.max_pos, VLTR_ERR_INVALID,
+             "opt_forward: prompt of %d tokens exceeds max_position_embeddings %d", max_len,
+             m->cfg.max_pos);
+  VLTR_CHECK(workspace != nullptr &&
+                 workspace_bytes >= vltr_opt_workspace_bytes(handle, num_tokens, num_prompts),
+             VLTR_ERR_INVALID, "opt_forward: workspace too small");
+  VLTR_CHECK((uintptr_t)workspace % 256 == 0, VLTR_ERR_INVALID,
+             "opt_forward: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m->cfg.dtype == VLTR_F16)
+    return opt::forward_t<__half>(*m, token_ids, positions, cu_seqlens, last_rows, num_tokens,
+                                  num_prompts, max_len, (char*)workspace, logits, s);
+  return opt::forward_t<__nv_bfloat16>(*m, token_ids, positions, cu_seqlens, last_rows, num_tokens,
+                                       num_prompts, max_len, (char*)workspace, logits, s);
+}
+
+extern "C" int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias,
+                             const void* resid, int M, int N, int K, int relu, int dtype,
+                             void* stream) {
+  return vltr::opt::gemm(A, W, D, bias, resid, M, N, K, relu, dtype, (cudaStream_t)stream);
+}

@@ -1,0 +1,272 @@
+"""The learning-to-rank predictor behind ``scheduler.aux_model``.
+
+The reference scores every new prompt once with an OPT-125M/350M sequence classifier by running a
+complete second engine (``AUXLLMEngine.obtain_aux_scores``, vllm/engine/aux_llm_engine.py:332-412:
+re-tokenise, build SequenceGroups, schedule, execute ``OPTForSequenceClassification`` through a
+worker, sample one dummy token, collect ``logits[:,0].tolist()``).  Only three things in that path
+are observable from the scheduler: which token ids the predictor sees (the prompt re-encoded with
+the predictor's tokenizer, truncated to ``max_model_len``), the model's logits, and the call
+``seq_group.set_aux_model_score(float)``.  ``B200AuxModel`` reproduces exactly those, with the
+forward pass done by ``libvllm_ltr_b200`` (csrc/opt_predictor.cu: tcgen05 GEMMs with fused
+epilogues, one stream, no host sync until the scores are read).
+
+    aux = B200AuxModel.from_pretrained(cfg.path, tokenizer=cfg.pred_model, max_length=cfg.max_length,
+                                       mtype=cfg.mtype)            # PrefillPredictorConfig fields
+    engine.scheduler.aux_model = aux                                # llm_engine.py:228-242
+"""
+import ctypes
+import json
+import os
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from ._lib import check, declare, lib
+
+MAX_LAYERS = 48
+F16, BF16 = 1, 2
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("hidden", "layers", "heads", "ffn", "vocab", "max_pos", "embed_dim", "num_labels",
+                 "do_layer_norm_before", "final_layer_norm", "dtype")]
+
+
+_PER_LAYER = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc1_w",
+              "fc1_b", "fc2_w", "fc2_b")
+
+
+class _Weights(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in
+                 ("embed_tokens", "embed_positions", "project_in", "project_out", "final_ln_w",
+                  "final_ln_b", "score")] +
+                [(n, ctypes.c_void_p * MAX_LAYERS) for n in _PER_LAYER])
+
+
+_P = ctypes.c_void_p
+declare("vltr_opt_create", ctypes.c_int, [ctypes.POINTER(_Config), ctypes.POINTER(_Weights),
+                                          ctypes.POINTER(ctypes.c_void_p)])
+declare("vltr_opt_destroy", None, [_P])
+declare("vltr_opt_workspace_bytes", ctypes.c_size_t, [_P, ctypes.c_int, ctypes.c_int])
+declare("vltr_opt_forward", ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, _P, ctypes.c_size_t, _P, _P])
+declare("vltr_opt_gemm", ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, _P])
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         resid: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """act(a @ w.T + bias) + resid on the tcgen05 path (the predictor's dense layer)."""
+    if not a.is_cuda:
+        raise RuntimeError("vllm_ltr_b200 predictor needs CUDA tensors (no CPU path)")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, dtype=a.dtype, device=a.device)
+    code = {torch.float16: F16, torch.bfloat16: BF16}.get(a.dtype)
+    if code is None:
+        raise RuntimeError(f"Unsupported data type: {a.dtype}")
+    with torch.cuda.device(a.device):
+        check(lib.vltr_opt_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(),
+                                bias.data_ptr() if bias is not None else None,
+                                resid.data_ptr() if resid is not None else None, m, n, k,
+                                1 if relu else 0, code,
+                                torch._C._cuda_getCurrentRawStream(a.device.index)))
+    return out
+
+
+class OPTPredictor:
+    """OPTForSequenceClassification forward (vllm/model_executor/models/opt.py:362-397) on the
+    GPU.  ``state_dict`` uses the HF checkpoint names the reference's load_weights consumes
+    (opt.py:411-444): ``model.decoder.layers.N.self_attn.q_proj.weight`` ... ``score.weight``."""
+
+    def __init__(self, config: Dict, state_dict: Dict[str, torch.Tensor], device="cuda:0",
+                 dtype: torch.dtype = torch.float16, max_batch_tokens: int = 2048,
+                 max_batch_prompts: int = 256):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vllm_ltr_b200 predictor needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.dtype = dtype
+        g = lambda k, d=None: config.get(k, d)
+        self.hidden = g("hidden_size")
+        self.layers = g("num_hidden_layers")
+        self.heads = g("num_attention_heads")
+        self.ffn = g("ffn_dim")
+        self.vocab = g("vocab_size")
+        self.max_pos = g("max_position_embeddings")
+        self.embed_dim = g("word_embed_proj_dim", self.hidden)
+        self.num_labels = g("num_labels", 1)
+        self.pre_ln = bool(g("do_layer_norm_before", True))
+        self.final_ln = self.pre_ln and not g("_remove_final_layer_norm", False)
+        if g("activation_function", "relu") != "relu":
+            raise RuntimeError("the LTR predictor checkpoints use ReLU (OPT); got "
+                               f"{g('activation_function')}")
+        # HF names: "model.decoder.*" + "score.weight"; older checkpoints drop the "model." prefix
+        # (the reference's loader accepts both, opt.py:421-424)
+        sd = {(k[len("model."):] if k.startswith("model.") else k): v
+              for k, v in state_dict.items()}
+        self._keep: List[torch.Tensor] = []
+
+        def dev(name, optional=False):
+            if name not in sd:
+                if optional:
+                    return None
+                raise KeyError(f"predictor checkpoint lacks {name}")
+            t = sd[name].detach().to(self.device, dtype).contiguous()
+            self._keep.append(t)
+            return t
+
+        def ptr(t):
+            return t.data_ptr() if t is not None else None
+
+        w = _Weights()
+        self.embed_tokens = dev("decoder.embed_tokens.weight")
+        w.embed_tokens = ptr(self.embed_tokens)
+        w.embed_positions = ptr(dev("decoder.embed_positions.weight"))
+        w.project_in = ptr(dev("decoder.project_in.weight", True))
+        w.project_out = ptr(dev("decoder.project_out.weight", True))
+        if (self.embed_dim != self.hidden) != (w.project_in is not None):
+            raise RuntimeError("project_in/project_out must exist iff word_embed_proj_dim != hidden")
+        if self.final_ln:
+            w.final_ln_w = ptr(dev("decoder.final_layer_norm.weight"))
+            w.final_ln_b = ptr(dev("decoder.final_layer_norm.bias"))
+        w.score = ptr(dev("score.weight"))
+        for i in range(self.layers):
+            p = f"decoder.layers.{i}."
+            qkv_w = torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], dim=0)
+            qkv_b = torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], dim=0)
+            sd[p + "qkv.weight"], sd[p + "qkv.bias"] = qkv_w, qkv_b
+            for field, name in (("ln1_w", "self_attn_layer_norm.weight"),
+                                ("ln1_b", "self_attn_layer_norm.bias"),
+                                ("qkv_w", "qkv.weight"), ("qkv_b", "qkv.bias"),
+                                ("out_w", "self_attn.out_proj.weight"),
+                                ("out_b", "self_attn.out_proj.bias"),
+                                ("ln2_w", "final_layer_norm.weight"),
+                                ("ln2_b", "final_layer_norm.bias"),
+                                ("fc1_w", "fc1.weight"), ("fc1_b", "fc1.bias"),
+                                ("fc2_w", "fc2.weight"), ("fc2_b", "fc2.bias")):
+                getattr(w, field)[i] = ptr(dev(p + name))
+        cfg = _Config(self.hidden, self.layers, self.heads, self.ffn, self.vocab, self.max_pos,
+                      self.embed_dim, self.num_labels, int(self.pre_ln), int(self.final_ln),
+                      F16 if dtype == torch.float16 else BF16)
+        self._handle = ctypes.c_void_p()
+        check(lib.vltr_opt_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(self._handle)))
+        self._weights = w
+        self.max_batch_tokens = max_batch_tokens
+        self.max_batch_prompts = max_batch_prompts
+        self._ws = None
+        self._ws_cap = (0, 0)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            lib.vltr_opt_destroy(h)
+            self._handle = None
+
+    @classmethod
+    def from_pretrained(cls, path: str, **kw) -> "OPTPredictor":
+        """Load an HF OPTForSequenceClassification checkpoint directory (what train/trainer.py
+        saves, :214-226): config.json + model.safetensors | pytorch_model.bin."""
+        with open(os.path.join(path, "config.json")) as f:
+            config = json.load(f)
+        st = os.path.join(path, "model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu",
+                            weights_only=True)
+        return cls(config, sd, **kw)
+
+    def _workspace(self, tokens: int, prompts: int):
+        if self._ws is None or tokens > self._ws_cap[0] or prompts > self._ws_cap[1]:
+            cap = (max(tokens, self._ws_cap[0], 256), max(prompts, self._ws_cap[1], 16))
+            n = lib.vltr_opt_workspace_bytes(self._handle, cap[0], cap[1])
+            self._ws = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
+            self._ws_cap = cap
+        off = (-self._ws.data_ptr()) % 256
+        return self._ws.data_ptr() + off, self._ws.numel() - off
+
+    def logits(self, prompts: Sequence[Sequence[int]]) -> torch.Tensor:
+        """[len(prompts), num_labels] float32 logits (values already rounded to the model dtype),
+        on the device.  Prompts are batched like the reference's aux scheduler does
+        (<= max(max_model_len, 2048) tokens and <= 256 prompts per forward, config.py:586)."""
+        out = torch.empty(len(prompts), self.num_labels, dtype=torch.float32, device=self.device)
+        i = 0
+        while i < len(prompts):
+            j, tok = i, 0
+            while (j < len(prompts) and j - i < self.max_batch_prompts
+                   and (j == i or tok + len(prompts[j]) <= self.max_batch_tokens)):
+                tok += len(prompts[j])
+                j += 1
+            self._forward(prompts[i:j], out[i:j])
+            i = j
+        return out
+
+    def _forward(self, batch: Sequence[Sequence[int]], out: torch.Tensor) -> None:
+        lens = [len(p) for p in batch]
+        if min(lens) < 1:
+            raise RuntimeError("empty prompt")
+        if max(lens) > self.max_pos:
+            raise RuntimeError(f"prompt of {max(lens)} tokens exceeds max_position_embeddings")
+        n, m = len(batch), sum(lens)
+        # one pinned staging buffer, one H2D copy: ids | positions | cu_seqlens | last_rows
+        host = torch.empty(2 * m + 2 * n + 1, dtype=torch.int32).pin_memory()
+        ids, pos = host[:m], host[m:2 * m]
+        cu, last = host[2 * m:2 * m + n + 1], host[2 * m + n + 1:]
+        o = 0
+        cu[0] = 0
+        for k, p in enumerate(batch):
+            ids[o:o + lens[k]] = torch.as_tensor(p, dtype=torch.int32)
+            pos[o:o + lens[k]] = torch.arange(lens[k], dtype=torch.int32)
+            o += lens[k]
+            cu[k + 1] = o
+            last[k] = o - 1
+        d = host.to(self.device, non_blocking=True)
+        ws, ws_bytes = self._workspace(m, n)
+        base = d.data_ptr()
+        with torch.cuda.device(self.device):
+            check(lib.vltr_opt_forward(self._handle, base, base + 4 * m, base + 8 * m,
+                                       base + 8 * m + 4 * (n + 1), m, n, max(lens), ws,
+                                       ctypes.c_size_t(ws_bytes), out.data_ptr(),
+                                       torch._C._cuda_getCurrentRawStream(self.device.index)))
+        self._last_inputs = d   # keep alive until the stream has consumed it
+
+    def scores(self, prompts: Sequence[Sequence[int]], mtype: str = "reg") -> List[float]:
+        """What the reference hands to the scheduler: ``logits[:,0].tolist()`` after
+        compute_logits (opt.py:389-409) - for classification heads the argmax label as float."""
+        lg = self.logits(prompts)
+        if self.num_labels > 1:
+            lg = lg[:, :self.num_labels].argmax(dim=-1, keepdim=True).float()
+        return lg[:, 0].tolist()
+
+
+class B200AuxModel:
+    """``scheduler.aux_model``: any object with ``obtain_aux_scores(seq_groups) -> List[float]``
+    that calls ``set_aux_model_score`` on each group (aux_llm_engine.py:332-412)."""
+
+    def __init__(self, predictor: OPTPredictor, tokenizer: Callable[[str], List[int]],
+                 max_length: int = 2048):
+        self.predictor = predictor
+        self.tokenizer = tokenizer
+        self.max_length = max_length
+
+    @classmethod
+    def from_pretrained(cls, path: str, tokenizer=None, max_length: int = 2048, **kw):
+        pred = OPTPredictor.from_pretrained(path, **kw)
+        if tokenizer is None or isinstance(tokenizer, str):
+            from transformers import AutoTokenizer
+            hf = AutoTokenizer.from_pretrained(tokenizer or path)
+            tokenizer = lambda text: hf.encode(text)
+        return cls(pred, tokenizer, max_length)
+
+    def obtain_aux_scores(self, seq_groups) -> List[float]:
+        prompts = []
+        for sg in seq_groups:
+            assert sg.need_aux_model_score()
+            text = sg.seqs_dict[next(iter(sg.seqs_dict))].prompt
+            prompts.append(list(self.tokenizer(text))[:self.max_length])
+        scores = self.predictor.scores(prompts)
+        for sg, s in zip(seq_groups, scores):
+            sg.set_aux_model_score(s)
+        return scores

@@ -12,6 +12,12 @@ for s in $STEPS; do
   case $s in
     smoke)   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke.log ;;
     tests)   timeout 1500 python -m pytest tests -q -m gpu --maxfail=60 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 $OUT/pytest_gpu.log ;;
+    predtest) timeout 300 python -m pytest tests/test_gpu_predictor.py -x -q -k "dense_layer" -p no:cacheprovider > $OUT/pred_gemm.log 2>&1; echo "pred gemm rc=$?"; tail -12 $OUT/pred_gemm.log
+              timeout 600 python -m pytest tests/test_gpu_predictor.py -x -q -k "not dense_layer" -p no:cacheprovider > $OUT/pred_fwd.log 2>&1; echo "pred fwd rc=$?"; tail -12 $OUT/pred_fwd.log ;;
+    newtests) timeout 900 python -m pytest tests/test_gpu_ltr.py tests/test_gpu_golden.py tests/test_gpu_cache.py -q -p no:cacheprovider > $OUT/newtests.log 2>&1; echo "newtests rc=$?"; tail -8 $OUT/newtests.log ;;
+    sweepcache) timeout 600 python tools/op_sweep.py --ops cache --json $OUT/sweep_cache.json > $OUT/sweep_cache.log 2>&1; echo "sweepcache rc=$?"; cat $OUT/sweep_cache.log ;;
+    attntests) timeout 1200 python -m pytest tests/test_gpu_attention.py tests/test_gpu_golden.py -q --maxfail=30 -p no:cacheprovider > $OUT/attntests.log 2>&1; echo "attntests rc=$?"; tail -40 $OUT/attntests.log ;;
+    sweepattn) timeout 900 python tools/op_sweep.py --ops attn --json $OUT/sweep_attn.json > $OUT/sweep_attn.log 2>&1; echo "sweepattn rc=$?"; cat $OUT/sweep_attn.log ;;
     golden)  timeout 600 python tests/golden/gen_golden_cuda.py $OUT/ref_cuda.npz > $OUT/golden.log 2>&1; echo "golden rc=$?"; tail -2 $OUT/golden.log ;;
     bench)   timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "benchref rc=$?"; cat $OUT/bench_ref.json ;;

@@ -2,12 +2,12 @@
 //
 // Replaces the launchers of csrc/attention/attention_kernels.cu (:628-778 v1, :809-975 v2) and the
 // v1/v2 choice made by the caller in vllm/attention/ops/paged_attn.py:101-110.  Both entry points
-// run the same kernel (attention_kernel.cuh); they differ in where partial results live:
-//   v1: no caller scratch.  Contexts are split only when that buys parallelism or trims the tail
-//       (few work items, or a long maximum context); partials then live in a library-owned fp32
-//       workspace and are merged by a second small kernel.
+// run the same single kernel (attention_kernel.cuh); they differ in where partial results live:
+//   v1: no caller scratch.  Contexts are cut into partitions sized so that the (sequence, kv head,
+//       partition) items fill the machine; partials of multi-partition sequences live in a
+//       library-owned fp32 workspace and are merged inside the kernel by the last finisher.
 //   v2: the caller's exp_sums / max_logits / tmp_out with the reference's 512-token partitions,
-//       left populated the way the reference leaves them.
+//       left populated the way the reference leaves them (merged in-kernel as well).
 #include <mutex>
 
 #include "attention_kernel.cuh"
@@ -21,18 +21,19 @@ int launch_mode_f32(Params&, int, int, cudaStream_t);
 int launch_mode_f16_fp8(Params&, int, int, cudaStream_t);
 int launch_mode_bf16_fp8(Params&, int, int, cudaStream_t);
 int launch_mode_f32_fp8(Params&, int, int, cudaStream_t);
-int reduce_f16(void*, const Params&, int, int, cudaStream_t);
-int reduce_bf16(void*, const Params&, int, int, cudaStream_t);
-int reduce_f32(void*, const Params&, int, int, cudaStream_t);
 
-// ---- per-device state: work-queue counters and the v1 split workspace ---------------------------
-constexpr int kCounterSlots = 64;
+// ---- per-device state: work-queue counters, partition tickets, v1 partial workspace -------------
+constexpr int kCounterSlots = 64;   // launches that may be in flight on different streams
 struct DevState {
   int* counters = nullptr;   // kCounterSlots x 2 ints, zero between launches (self-resetting)
   unsigned next_slot = 0;
+  int* tickets = nullptr;    // kTicketSlots regions of ticket_cap ints, all zero between launches
+  size_t ticket_cap = 0;
+  unsigned next_ticket = 0;
   char* ws = nullptr;        // grow-only
   size_t ws_bytes = 0;
 };
+constexpr int kTicketSlots = 8;
 static DevState g_dev[64];
 static std::mutex g_mu;
 
@@ -49,9 +50,9 @@ static int get_state(DevState** out) {
   return VLTR_OK;
 }
 
+// grow-only buffers; growing frees the old one after the device drains (first calls only)
 static int ensure_ws(DevState* st, size_t bytes) {
   if (st->ws_bytes >= bytes) return VLTR_OK;
-  // grow-only; growing frees the old buffer after the device drains (rare: first calls only)
   if (st->ws != nullptr) {
     VLTR_CUDA(cudaDeviceSynchronize());
     VLTR_CUDA(cudaFree(st->ws));
@@ -61,6 +62,20 @@ static int ensure_ws(DevState* st, size_t bytes) {
   size_t cap = bytes + bytes / 2;
   VLTR_CUDA(cudaMalloc(&st->ws, cap));
   st->ws_bytes = cap;
+  return VLTR_OK;
+}
+static int ensure_tickets(DevState* st, size_t n) {
+  if (st->ticket_cap >= n) return VLTR_OK;
+  if (st->tickets != nullptr) {
+    VLTR_CUDA(cudaDeviceSynchronize());
+    VLTR_CUDA(cudaFree(st->tickets));
+    st->tickets = nullptr;
+    st->ticket_cap = 0;
+  }
+  size_t cap = n < 4096 ? 4096 : n + n / 2;
+  VLTR_CUDA(cudaMalloc(&st->tickets, sizeof(int) * cap * kTicketSlots));
+  VLTR_CUDA(cudaMemset(st->tickets, 0, sizeof(int) * cap * kTicketSlots));
+  st->ticket_cap = cap;
   return VLTR_OK;
 }
 
@@ -78,9 +93,10 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
              num_kv_heads);
   VLTR_CHECK(dtype == VLTR_F32 || dtype == VLTR_F16 || dtype == VLTR_BF16, VLTR_ERR_UNSUPPORTED,
              "Unsupported data type: %d", dtype);
+  VLTR_CHECK(block_size == 8 || block_size == 16 || block_size == 32, VLTR_ERR_UNSUPPORTED,
+             "Unsupported block size: %d", block_size);
   if (num_seqs == 0) return VLTR_OK;
   const int cs = kv_fp8 ? 1 : (dtype == VLTR_F32 ? 4 : 2);
-  const int as = dtype == VLTR_F32 ? 4 : 2;
   VLTR_CHECK(kv_head_stride == (int64_t)head_size * block_size, VLTR_ERR_INVALID,
              "paged_attention: a (block, head) KV tile must be contiguous (kv_head_stride %lld != "
              "head_size*block_size %d)",
@@ -88,7 +104,8 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
   VLTR_CHECK(((uintptr_t)key_cache % 16 == 0) && ((uintptr_t)value_cache % 16 == 0) &&
                  (kv_block_stride * cs) % 16 == 0 && (kv_head_stride * cs) % 16 == 0,
              VLTR_ERR_INVALID, "paged_attention: KV cache must be 16-byte aligned");
-  (void)as;
+  VLTR_CHECK((uintptr_t)query % 16 == 0 && (q_stride * (dtype == VLTR_F32 ? 4 : 2)) % 16 == 0,
+             VLTR_ERR_INVALID, "paged_attention: query rows must be 16-byte aligned");
 
   DevState* st = nullptr;
   {
@@ -114,55 +131,57 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
   p.q_stride = q_stride;
   p.kv_block_stride = kv_block_stride * cs;
   p.kv_head_stride = kv_head_stride * cs;
+  p.use_plan = num_seqs <= kMaxPlanSeqs;
+
+  // query heads per work item: G == 1 (or fp32) runs the FMA path one head group at a time, GQA
+  // groups ride the 16 rows of the tensor-core tile
+  const int G = p.group;
+  const bool mma = dtype != VLTR_F32 && G >= 2;
+  int gt;
+  if (mma) gt = G <= 8 ? 8 : 16;
+  else gt = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
+  // (the FMA instantiations cap gt by register budget; launch_gt() may lower it)
+  p.passes = (G + gt - 1) / gt;
 
   const int max_blocks = (max_context_len + block_size - 1) / block_size;
-  int part_tokens = 0;
   if (v2) {
     // reference partitioning: PARTITION_SIZE = 512 (attention_kernels.cu:815,858)
-    VLTR_CHECK(512 % block_size == 0, VLTR_ERR_UNSUPPORTED, "Unsupported block size: %d",
-               block_size);
-    part_tokens = 512;
+    p.part_blocks = 512 / block_size;
     p.n_part = (max_context_len + 511) / 512;
     if (p.n_part < 1) p.n_part = 1;
-    p.part_blocks = 512 / block_size;
-    p.split = 1;
+    p.always_partial = 1;
     p.tmp_is_f32 = dtype == VLTR_F32;
     p.exp_sums = exp_sums;
     p.max_logits = max_logits;
     p.tmp_out = tmp_out;
   } else {
-    // split when the (seq, kv_head) items cannot fill the machine, or when one long context
-    // would become the tail of the launch
-    const int slots = num_sms() * 8;
-    const long long items = (long long)num_seqs * num_kv_heads;
-    int want = 1;
-    if (items < 2LL * slots) want = (int)((2LL * slots + items - 1) / items);
-    if (max_context_len > 2048) {
-      const int by_len = (max_context_len + 1023) / 1024;
-      if (by_len > want) want = by_len;
-    }
-    int pb = (max_blocks + want - 1) / want;                 // blocks per partition
-    const int min_pb = (256 + block_size - 1) / block_size;  // at least 256 tokens
-    if (pb < min_pb) pb = min_pb;
+    // partition size: enough (sequence, kv head, pass, partition) items for ~3 per resident
+    // warp, at most 512 tokens (one lane-held window of block ids per item, and a short tail),
+    // at least 64 tokens, and no more than 64 partitions per sequence
+    const long long slots = (long long)num_sms() * 8;
+    const long long groups = (long long)num_seqs * num_kv_heads * p.passes;
+    long long parts_wanted = (3 * slots + groups - 1) / groups;
+    if (parts_wanted < 1) parts_wanted = 1;
+    long long pt = (max_context_len + parts_wanted - 1) / parts_wanted;
+    const long long pt_min = (max_context_len + 63) / 64;
+    if (pt < pt_min) pt = pt_min;
+    if (pt < 64) pt = 64;
+    int cap = 32 * block_size;
+    if (cap > 512) cap = 512;
+    if (pt > cap) pt = cap;
+    int pb = (int)((pt + block_size - 1) / block_size);
     if (pb < 1) pb = 1;
-    const int n_part = max_blocks > 0 ? (max_blocks + pb - 1) / pb : 1;
-    if (n_part <= 1) {
-      p.n_part = 1;
-      p.part_blocks = max_blocks > 0 ? max_blocks : 1;
-      p.split = 0;
-    } else {
-      p.n_part = n_part;
-      p.part_blocks = pb;
-      part_tokens = pb * block_size;
-      p.split = 1;
-      p.tmp_is_f32 = 1;
-      const size_t n = (size_t)num_seqs * num_heads * n_part;
+    if (pb > 64) pb = 64;
+    p.part_blocks = pb;
+    p.n_part = max_blocks > 0 ? (max_blocks + pb - 1) / pb : 1;
+    p.always_partial = 0;
+    p.tmp_is_f32 = 1;
+    if (p.n_part > 1) {
+      const size_t n = (size_t)num_seqs * num_heads * p.n_part;
       const size_t bytes = n * sizeof(float) * 2 + n * head_size * sizeof(float);
-      {
-        std::lock_guard<std::mutex> lk(g_mu);
-        int rc = ensure_ws(st, bytes);
-        if (rc) return rc;
-      }
+      std::lock_guard<std::mutex> lk(g_mu);
+      int rc = ensure_ws(st, bytes);
+      if (rc) return rc;
       p.exp_sums = reinterpret_cast<float*>(st->ws);
       p.max_logits = p.exp_sums + n;
       p.tmp_out = p.max_logits + n;
@@ -170,26 +189,23 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
   }
   {
     std::lock_guard<std::mutex> lk(g_mu);
+    const size_t ngroups = (size_t)num_seqs * num_kv_heads * 16;   // passes <= 16 for any sane G
+    int rc = ensure_tickets(st, ngroups);
+    if (rc) return rc;
+    p.tickets = st->tickets + (size_t)(st->next_ticket++ % kTicketSlots) * st->ticket_cap;
     p.counters = st->counters + 2 * (st->next_slot++ % kCounterSlots);
   }
+  VLTR_CHECK((long long)num_seqs * num_kv_heads * p.passes <= (long long)st->ticket_cap,
+             VLTR_ERR_INVALID, "paged_attention: too many head groups");
 
-  int rc;
   if (!kv_fp8) {
-    rc = dtype == VLTR_F16    ? launch_mode_f16(p, head_size, block_size, stream)
-         : dtype == VLTR_BF16 ? launch_mode_bf16(p, head_size, block_size, stream)
-                              : launch_mode_f32(p, head_size, block_size, stream);
-  } else {
-    rc = dtype == VLTR_F16    ? launch_mode_f16_fp8(p, head_size, block_size, stream)
+    return dtype == VLTR_F16    ? launch_mode_f16(p, head_size, block_size, stream)
+           : dtype == VLTR_BF16 ? launch_mode_bf16(p, head_size, block_size, stream)
+                                : launch_mode_f32(p, head_size, block_size, stream);
+  }
+  return dtype == VLTR_F16    ? launch_mode_f16_fp8(p, head_size, block_size, stream)
          : dtype == VLTR_BF16 ? launch_mode_bf16_fp8(p, head_size, block_size, stream)
                               : launch_mode_f32_fp8(p, head_size, block_size, stream);
-  }
-  if (rc) return rc;
-  if (p.split) {
-    rc = dtype == VLTR_F16    ? reduce_f16(out, p, head_size, part_tokens, stream)
-         : dtype == VLTR_BF16 ? reduce_bf16(out, p, head_size, part_tokens, stream)
-                              : reduce_f32(out, p, head_size, part_tokens, stream);
-  }
-  return rc;
 }
 
 }  // namespace attn

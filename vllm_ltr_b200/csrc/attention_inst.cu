@@ -11,22 +11,23 @@
 namespace vltr {
 namespace attn {
 
-template <typename T, typename CT, int D, int BS, int GT>
-static int launch_one(const Params& p0, int num_items_hint, cudaStream_t stream) {
-  using C = Cfg<T, CT, D, BS, GT>;
-  auto kern = paged_attention_kernel<T, CT, D, BS, GT>;
+template <typename T, typename CT, int D, int BS, int GT, bool MMA>
+static int launch_one(const Params& p0, cudaStream_t stream) {
+  using C = Cfg<T, CT, D, BS, GT, MMA>;
+  auto kern = paged_attention_kernel<T, CT, D, BS, GT, MMA>;
   // per-instantiation launch plan, computed once: stages, warps/CTA, CTAs/SM
   struct Plan { int stages, warps, smem, ctas_per_sm; bool ok; };
+  constexpr int kPlanBytes = (kMaxPlanSeqs + 1) * 4;
   static Plan plan = [&]() {
     Plan pl{0, 0, 0, 0, false};
     int dev = 0, max_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     // target two 4-warp CTAs per SM; shrink warps/CTA when tiles are too large for that
-    const int budget = (max_optin - 2048) / 2;
+    const int budget = (max_optin - 2048) / 2 - kPlanBytes;
     int warps = 4, stages = 0;
     for (; warps >= 1; warps >>= 1) {
-      const int lim = warps == 4 ? budget : max_optin;
+      const int lim = warps == 4 ? budget : max_optin - kPlanBytes;
       for (stages = 6; stages >= 2; --stages)
         if (warps * warp_smem_bytes<C>(stages) <= lim) break;
       if (stages >= 2) break;
@@ -34,7 +35,7 @@ static int launch_one(const Params& p0, int num_items_hint, cudaStream_t stream)
     if (warps < 1 || stages < 2) return pl;
     pl.stages = stages;
     pl.warps = warps;
-    pl.smem = warps * warp_smem_bytes<C>(stages);
+    pl.smem = warps * warp_smem_bytes<C>(stages) + kPlanBytes;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem) !=
         cudaSuccess) {
       cudaGetLastError();
@@ -50,59 +51,77 @@ static int launch_one(const Params& p0, int num_items_hint, cudaStream_t stream)
   Params p = p0;
   p.stages = plan.stages;
   int grid = num_sms() * plan.ctas_per_sm;
-  const int need = (p.total_items + plan.warps - 1) / plan.warps;
-  if (grid > need) grid = need;
+  const long long items_ub = (long long)p.num_seqs * p.n_part * p.passes * p.num_kv_heads;
+  const long long need = (items_ub + plan.warps - 1) / plan.warps;
+  if (grid > need) grid = (int)need;
   if (grid < 1) grid = 1;
-  (void)num_items_hint;
   kern<<<grid, plan.warps * 32, plan.smem, stream>>>(p);
   VLTR_LAUNCH_CHECK("paged_attention");
   return VLTR_OK;
 }
 
-// largest head-group tile that keeps the accumulators in registers (GT * RI <= 64)
+// largest head-group tile of the FMA path that keeps the accumulators in registers (GT * RI <= 64)
 template <typename T, typename CT, int D, int BS>
 static constexpr int gt_cap() {
-  constexpr int RI = Cfg<T, CT, D, BS, 1>::RI;
+  constexpr int RI = Cfg<T, CT, D, BS, 1, false>::RI;
   return RI <= 8 ? 8 : (RI <= 16 ? 4 : (RI <= 32 ? 2 : 1));
 }
 
 template <typename T, typename CT, int D, int BS>
 static int launch_gt(Params& p, cudaStream_t stream) {
-  constexpr int CAP = gt_cap<T, CT, D, BS>();
   const int G = p.group;
-  int gt = G <= 1 ? 1 : (G <= 4 ? 4 : 8);
-  if (gt > CAP) gt = CAP;
-  p.passes = (G + gt - 1) / gt;
-  p.total_items = p.num_seqs * p.n_part * p.passes * p.num_kv_heads;
-  switch (gt) {
-    case 1: return launch_one<T, CT, D, BS, 1>(p, 0, stream);
-    case 2:
-      if constexpr (CAP >= 2 && CAP < 4) return launch_one<T, CT, D, BS, 2>(p, 0, stream);
-      break;
-    case 4:
-      if constexpr (CAP >= 4) return launch_one<T, CT, D, BS, 4>(p, 0, stream);
-      break;
-    case 8:
-      if constexpr (CAP >= 8) return launch_one<T, CT, D, BS, 8>(p, 0, stream);
-      break;
+  if constexpr (sizeof(T) == 2) {
+    if (G >= 2) {   // tensor-core path
+      const int gt = G <= 8 ? 8 : 16;
+      p.passes = (G + gt - 1) / gt;
+      if (gt == 8) return launch_one<T, CT, D, BS, 8, true>(p, stream);
+      return launch_one<T, CT, D, BS, 16, true>(p, stream);
+    }
+    if constexpr (BS % (16 / (int)sizeof(CT)) != 0) {
+      // e5m2 cache with block size 8: a V row is half a 16-byte chunk; the FMA path cannot tile
+      // it, the tensor-core path can (G == 1 rides row 0 of the tile)
+      p.passes = 1;
+      return launch_one<T, CT, D, BS, 8, true>(p, stream);
+    } else {
+      p.passes = 1;
+      return launch_one<T, CT, D, BS, 1, false>(p, stream);
+    }
+  } else {
+    if constexpr (BS % (16 / (int)sizeof(CT)) != 0) {
+      return fail(VLTR_ERR_UNSUPPORTED,
+                  "Unsupported block size: %d for fp32 queries with an fp8 kv cache", BS);
+    } else {
+      constexpr int CAP = gt_cap<T, CT, D, BS>();
+      int gt = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
+      if (gt > CAP) gt = CAP;
+      p.passes = (G + gt - 1) / gt;
+      switch (gt) {
+        case 1: return launch_one<T, CT, D, BS, 1, false>(p, stream);
+        case 2:
+          if constexpr (CAP >= 2) return launch_one<T, CT, D, BS, 2, false>(p, stream);
+          break;
+        case 4:
+          if constexpr (CAP >= 4) return launch_one<T, CT, D, BS, 4, false>(p, stream);
+          break;
+        case 8:
+          if constexpr (CAP >= 8) return launch_one<T, CT, D, BS, 8, false>(p, stream);
+          break;
+      }
+      return fail(VLTR_ERR_UNSUPPORTED, "paged_attention: no kernel for group tile %d", gt);
+    }
   }
-  return fail(VLTR_ERR_UNSUPPORTED, "paged_attention: no kernel for group tile %d", gt);
 }
 
 template <typename T, typename CT, int BS>
 static int launch_d(Params& p, int head_size, cudaStream_t stream) {
-  if constexpr (BS % (16 / (int)sizeof(CT)) != 0) {
-    return fail(VLTR_ERR_UNSUPPORTED, "Unsupported block size: %d for this kv cache dtype", BS);
-  } else {
-    switch (head_size) {
-      case 64: return launch_gt<T, CT, 64, BS>(p, stream);
-      case 80: return launch_gt<T, CT, 80, BS>(p, stream);
-      case 96: return launch_gt<T, CT, 96, BS>(p, stream);
-      case 112: return launch_gt<T, CT, 112, BS>(p, stream);
-      case 128: return launch_gt<T, CT, 128, BS>(p, stream);
-      case 256: return launch_gt<T, CT, 256, BS>(p, stream);
-      default: return fail(VLTR_ERR_UNSUPPORTED, "Unsupported head size: %d", head_size);
-    }
+  switch (head_size) {
+    case 64: return launch_gt<T, CT, 64, BS>(p, stream);
+    case 80: return launch_gt<T, CT, 80, BS>(p, stream);
+    case 96: return launch_gt<T, CT, 96, BS>(p, stream);
+    case 112: return launch_gt<T, CT, 112, BS>(p, stream);
+    case 128: return launch_gt<T, CT, 128, BS>(p, stream);
+    case 256: return launch_gt<T, CT, 256, BS>(p, stream);
+    default: return fail(VLTR_ERR_UNSUPPORTED, "Unsupported head size: %d", head_size);
   }
 }
 
@@ -116,49 +135,17 @@ static int launch_bs(Params& p, int head_size, int block_size, cudaStream_t stre
   }
 }
 
-template <typename T, typename PT>
-static int launch_reduce_d(void* out, const Params& p, int head_size, int part_tokens,
-                           cudaStream_t stream) {
-  const int total = p.num_seqs * p.num_heads;
-  const int grid = (total + 3) / 4;
-#define VLTR_RED(DD)                                                                         \
-  case DD:                                                                                   \
-    paged_attention_reduce_kernel<T, PT, DD><<<grid, 128, 0, stream>>>(                      \
-        (T*)out, p.exp_sums, p.max_logits, (const PT*)p.tmp_out, p.context_lens, p.num_heads, \
-        p.n_part, part_tokens, total);                                                       \
-    break;
-  switch (head_size) {
-    VLTR_RED(64) VLTR_RED(80) VLTR_RED(96) VLTR_RED(112) VLTR_RED(128) VLTR_RED(256)
-    default: return fail(VLTR_ERR_UNSUPPORTED, "Unsupported head size: %d", head_size);
-  }
-#undef VLTR_RED
-  VLTR_LAUNCH_CHECK("paged_attention_reduce");
-  return VLTR_OK;
-}
-
 #if VLTR_ATTN_MODE == 0
 int launch_mode_f16(Params& p, int head_size, int block_size, cudaStream_t s) {
   return launch_bs<__half, __half>(p, head_size, block_size, s);
-}
-int reduce_f16(void* out, const Params& p, int head_size, int part_tokens, cudaStream_t s) {
-  return p.tmp_is_f32 ? launch_reduce_d<__half, float>(out, p, head_size, part_tokens, s)
-                      : launch_reduce_d<__half, __half>(out, p, head_size, part_tokens, s);
 }
 #elif VLTR_ATTN_MODE == 1
 int launch_mode_bf16(Params& p, int head_size, int block_size, cudaStream_t s) {
   return launch_bs<__nv_bfloat16, __nv_bfloat16>(p, head_size, block_size, s);
 }
-int reduce_bf16(void* out, const Params& p, int head_size, int part_tokens, cudaStream_t s) {
-  return p.tmp_is_f32
-             ? launch_reduce_d<__nv_bfloat16, float>(out, p, head_size, part_tokens, s)
-             : launch_reduce_d<__nv_bfloat16, __nv_bfloat16>(out, p, head_size, part_tokens, s);
-}
 #elif VLTR_ATTN_MODE == 2
 int launch_mode_f32(Params& p, int head_size, int block_size, cudaStream_t s) {
   return launch_bs<float, float>(p, head_size, block_size, s);
-}
-int reduce_f32(void* out, const Params& p, int head_size, int part_tokens, cudaStream_t s) {
-  return launch_reduce_d<float, float>(out, p, head_size, part_tokens, s);
 }
 #elif VLTR_ATTN_MODE == 3
 int launch_mode_f16_fp8(Params& p, int head_size, int block_size, cudaStream_t s) {

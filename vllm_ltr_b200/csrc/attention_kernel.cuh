@@ -13,15 +13,22 @@
 //   8-byte LDG of K straight from global,       each (block, kv_head) K tile and V tile is one
 //   no staging, no async copy                   contiguous span: moved HBM->smem by TMA bulk
 //                                               copies (cp.async.bulk, SASS UBLKCP) into a
-//                                               per-warp mbarrier ring, 128-bit LDS from there
-//   logits for the whole context in smem        online softmax per 1 KV block in registers:
+//                                               per-warp mbarrier ring that runs ACROSS work
+//                                               items (the next item's tiles are already in
+//                                               flight while the current one finishes)
+//   logits for the whole context in smem        online softmax per KV block in registers:
 //   (4*ctx bytes -> 8K..57K token limit),       no context-length limit, no CTA-wide barrier
 //   3 __syncthreads + smem tree per CTA         in the main loop (warps are independent)
-//   q.k with cvt f16->f32 + FFMA; p.v in        FHFMA (fma.rn.f32.f16 / .bf16, sm_100 mixed
-//   half precision (mul.f16x2)                  precision FMA): f16/bf16 operands straight from
-//                                               smem, fp32 accumulation, no conversions
-//   static grid, tail effects on ragged         persistent grid (CTAs/SM x 148), warps pull
-//   context lengths                             items from an atomic queue (self-resetting)
+//   q.k with cvt f16->f32 + FFMA; p.v in        G == 1: FHFMA (fma.rn.f32.f16/.bf16, sm_100
+//   half precision (mul.f16x2)                  mixed-precision FMA), fp32 accumulation.
+//                                               G >= 2: the G query heads of a kv head form the
+//                                               M rows of mma.sync.m16n8k16 (K / V fragments by
+//                                               ldmatrix straight from the paged tile layout),
+//                                               so a KV byte costs ~10x fewer instructions
+//   static grid; v2 = second kernel that        persistent grid; contexts are cut into
+//   merges 512-token partitions through         partitions sized to fill the machine, a seq's
+//   global memory                               partitions are merged by whichever warp finishes
+//                                               LAST (atomic ticket) - one launch, no tail
 //
 // Bound: HBM.  Algorithmic bytes per call = sum_i L_i*2*Hkv*D*s_cache + q + out + tables.
 #pragma once
@@ -35,6 +42,7 @@ namespace attn {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kMaxPlanSeqs = 2048;   // per-CTA partition plan (prefix sums) lives in smem up to here
 
 struct Params {
   void* out;                    // [num_seqs, num_heads, D]  T
@@ -44,22 +52,24 @@ struct Params {
   const int32_t* block_tables;  // [num_seqs, max_blocks_per_seq]
   const int32_t* context_lens;  // [num_seqs]
   const float* alibi_slopes;    // [num_heads] or null
-  // split mode (n_part > 1 or v2): partial results
+  // partial results of partitioned contexts
   float* exp_sums;              // [num_seqs, num_heads, n_part]
   float* max_logits;            // [num_seqs, num_heads, n_part]
-  void* tmp_out;                // [num_seqs, num_heads, n_part, D]  T or float
-  int split;                    // 0: write `out`, 1: write partials
+  void* tmp_out;                // [num_seqs, num_heads, n_part, D]  T (v2 caller scratch) or float
+  int always_partial;           // v2: fill the caller's partials even for single-partition seqs
   int tmp_is_f32;
   int num_seqs, num_heads, num_kv_heads, group, passes;
   int max_blocks_per_seq;
-  int n_part, part_blocks;
+  int n_part;                   // partitions of the longest context (second-to-last tmp dim)
+  int part_blocks;              // KV blocks per partition (<= 64)
   float scale;
   int64_t q_stride;             // elements
   int64_t kv_block_stride;      // bytes
   int64_t kv_head_stride;       // bytes
-  int total_items;
   int stages;
-  int* counters;                // [0] next item, [1] finished warps
+  int use_plan;                 // 1: items enumerate only non-empty partitions (num_seqs <= kMaxPlanSeqs)
+  int* counters;                // [0] next item, [1] finished warps   (self-resetting)
+  int* tickets;                 // [num_seqs * passes * num_kv_heads] partition tickets, all zero
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -102,6 +112,16 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
                : "r"(addr));
   return r;
 }
+__device__ __forceinline__ uint32_t lds4(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
 
 // mixed-precision FMA (sm_100): d = a.f16 * b.f16 + c.f32, both halves of a packed word
 template <typename T>
@@ -129,27 +149,76 @@ __device__ __forceinline__ float fhfma2<__nv_bfloat16>(uint32_t a, uint32_t b, f
   return r;
 }
 
+// D(16x8, f32) += A(16x16) * B(16x8); MT = __half or __nv_bfloat16 operands
+template <typename MT>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  if constexpr (std::is_same<MT, __half>::value) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+template <typename MT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if constexpr (std::is_same<MT, __half>::value) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+template <typename MT>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if constexpr (std::is_same<MT, __half>::value)
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  else
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
 // ---- compile-time geometry ------------------------------------------------------------------------
-template <typename T, typename CT, int D_, int BS_, int GT_>
+// GT: query heads handled per work item ("pass").  MMA: tensor-core path (GT = 8 or 16 rows).
+template <typename T, typename CT, int D_, int BS_, int GT_, bool MMA_>
 struct Cfg {
   static constexpr int D = D_, BS = BS_, GT = GT_;
+  static constexpr bool MMA = MMA_;
   static constexpr bool FP8 = !std::is_same<T, CT>::value;
   static constexpr int EPC = 16 / sizeof(CT);       // elements per 16-byte cache chunk (== x)
   static constexpr int NCH = D / EPC;               // K chunks per token
-  static constexpr int TG = 32 / BS;                // lanes sharing one token in q.k
+  static constexpr int TG = 32 / BS;                // lanes sharing one token in q.k (FMA path)
   static constexpr int KJ = (NCH + TG - 1) / TG;    // K chunks per lane
   static constexpr int LPR = BS / EPC;              // lanes sharing one V row
-  static constexpr int RPI = 32 / LPR;              // V rows per iteration
+  static constexpr int RPI = 32 / (LPR > 0 ? LPR : 1);  // V rows per iteration
   static constexpr int RI = (D + RPI - 1) / RPI;    // V row iterations per lane
   static constexpr bool HALF = std::is_same<T, __half>::value;
   static constexpr bool PACKED = HALF || (std::is_same<T, __nv_bfloat16>::value && !FP8);
-  using QS = typename std::conditional<PACKED, T, float>::type;   // q / p storage in smem
+  using QS = typename std::conditional<PACKED, T, float>::type;   // q / p storage in smem (FMA)
+  // tensor-core operand type: the cache type for 2-byte caches, f16 for e5m2 caches (e5m2 -> f16
+  // is a byte shift; a bf16 query converts to f16 exactly in the normal range)
+  using MT = typename std::conditional<FP8, __half, T>::type;
   static constexpr int QW = EPC * sizeof(QS) / 16;  // 16-byte words of q (or p) per cache chunk
   static constexpr int TILE_BYTES = D * BS * (int)sizeof(CT);
-  static constexpr int Q_BYTES = GT * D * (int)sizeof(QS);
-  static constexpr int P_BYTES = GT * BS * (int)sizeof(QS);
+  static constexpr int Q_BYTES = MMA ? 0 : GT * D * (int)sizeof(QS);
+  static constexpr int P_BYTES = MMA ? 0 : GT * BS * (int)sizeof(QS);
   static constexpr bool P_IN_REGS = GT * QW <= 8;
-  static_assert(D % EPC == 0 && BS % EPC == 0 && LPR >= 1 && 32 % BS == 0, "geometry");
+  static constexpr int NT = BS / 8;                 // MMA: n-tiles (8 tokens) per KV block
+  static constexpr int KS = D / 16;                 // MMA: k-steps of q.k
+  static constexpr int ND = D / 8;                  // MMA: n-tiles of p.v
+  static constexpr int KT = (BS + 15) / 16;         // MMA: k-steps of p.v
+  static constexpr bool R16 = GT > 8;               // MMA: rows 8..15 of the tile are live
+  static_assert(D % EPC == 0 && 32 % BS == 0, "geometry");
+  static_assert(!MMA || (D % 16 == 0 && (GT == 8 || GT == 16) && sizeof(T) == 2), "mma geometry");
+  static_assert(MMA || (BS % EPC == 0), "fma path needs whole 16-byte chunks per V row");
 };
 
 template <typename C>
@@ -158,7 +227,7 @@ __host__ __device__ constexpr int warp_smem_bytes(int stages) {
          ((stages * 8 + 15) / 16) * 16;
 }
 
-// acc += dot(one 16-byte cache chunk, the matching q (or p) words)
+// acc += dot(one 16-byte cache chunk, the matching q (or p) words)            (FMA path)
 template <typename T, typename C>
 __device__ __forceinline__ float dot_chunk(float acc, const uint4& kv, const uint4* qw) {
   const uint32_t k[4] = {kv.x, kv.y, kv.z, kv.w};
@@ -230,99 +299,150 @@ __device__ __forceinline__ float qs_to_f<__nv_bfloat16>(__nv_bfloat16 x) {
   return __bfloat162float(x);
 }
 
+// L2 (cache-global) load of one T as float: partials written by other SMs in this launch
+template <typename T>
+__device__ __forceinline__ float load_cg_f(const T* ptr) {
+  if constexpr (sizeof(T) == 4) {
+    return __ldcg(reinterpret_cast<const float*>(ptr));
+  } else {
+    const unsigned short raw = __ldcg(reinterpret_cast<const unsigned short*>(ptr));
+    if constexpr (std::is_same<T, __half>::value)
+      return __half2float(__ushort_as_half(raw));
+    else
+      return __bfloat162float(__ushort_as_bfloat16(raw));
+  }
+}
+
+// ---- work items -----------------------------------------------------------------------------------
+// One item = one partition of one sequence for one kv head and one pass over its query heads.
+struct Item {
+  int valid;            // 0: queue exhausted
+  int seq, part, pass, kvh;
+  int ctx, nparts;      // context length and number of partitions of this sequence
+  int blk0, ntiles;     // first KV block and number of KV blocks of this partition
+  int issued;           // tiles handed to the TMA ring so far
+  int bt0, bt1;         // lane i holds the block ids of tiles i and 32+i
+};
+
+// cum[s] = number of partitions of sequences < s (plan mode), in shared memory
+__device__ __forceinline__ void claim(Item& it, const Params& p, const int* cum, int total_items,
+                                      int part_tokens, int BS, int lane) {
+  int item = 0;
+  if (lane == 0) item = atomicAdd(&p.counters[0], 1);
+  item = __shfl_sync(0xffffffffu, item, 0);
+  it.valid = item < total_items;
+  it.issued = 0;
+  it.ntiles = 0;
+  if (!it.valid) return;
+  it.kvh = item % p.num_kv_heads;
+  int t = item / p.num_kv_heads;
+  it.pass = t % p.passes;
+  t /= p.passes;
+  if (p.use_plan) {
+    // largest s with cum[s] <= t
+    int lo = 0, hi = p.num_seqs;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid] <= t) lo = mid; else hi = mid;
+    }
+    it.seq = lo;
+    it.part = t - cum[lo];
+  } else {
+    it.part = t % p.n_part;
+    it.seq = t / p.n_part;
+  }
+  it.ctx = p.context_lens[it.seq];
+  const int nblk_ctx = (it.ctx + BS - 1) / BS;
+  it.nparts = (it.ctx + part_tokens - 1) / part_tokens;
+  it.blk0 = it.part * p.part_blocks;
+  const int blk1 = min(it.blk0 + p.part_blocks, nblk_ctx);
+  it.ntiles = max(blk1 - it.blk0, 0);
+  const int32_t* bt = p.block_tables + (int64_t)it.seq * p.max_blocks_per_seq + it.blk0;
+  it.bt0 = lane < it.ntiles ? bt[lane] : 0;
+  it.bt1 = 32 + lane < it.ntiles ? bt[32 + lane] : 0;
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------
-template <typename T, typename CT, int D, int BS, int GT>
+template <typename T, typename CT, int D, int BS, int GT, bool MMA>
 __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_constant__ Params p) {
-  using C = Cfg<T, CT, D, BS, GT>;
+  using C = Cfg<T, CT, D, BS, GT, MMA>;
   using QS = typename C::QS;
+  using MT = typename C::MT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   const int S = p.stages;
   const int wbytes = warp_smem_bytes<C>(S);
   unsigned char* wbase = smem_raw + (size_t)warp * wbytes;
   const uint32_t tiles_s = smem_u32(wbase);                        // S x {K tile, V tile}
-  QS* q_s = reinterpret_cast<QS*>(wbase + S * 2 * C::TILE_BYTES);  // [GT][D]
+  QS* q_s = reinterpret_cast<QS*>(wbase + S * 2 * C::TILE_BYTES);  // [GT][D]      (FMA path)
   QS* p_s = reinterpret_cast<QS*>(reinterpret_cast<unsigned char*>(q_s) +
-                                  ((C::Q_BYTES + 15) / 16) * 16);  // [GT][BS]
+                                  ((C::Q_BYTES + 15) / 16) * 16);  // [GT][BS]     (FMA path)
   const uint32_t bars = smem_u32(reinterpret_cast<unsigned char*>(p_s) +
                                  ((C::P_BYTES + 15) / 16) * 16);   // S mbarriers
   const uint32_t q_sa = smem_u32(q_s), p_sa = smem_u32(p_s);
+  int* cum = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * wbytes);   // [num_seqs + 1]
 
   if (lane == 0) {
     for (int s = 0; s < S; ++s) mbar_init(bars + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  const int part_tokens = p.part_blocks * BS;
+  int total_items;
+  if (p.use_plan) {
+    // partition plan: exclusive prefix sums of the per-sequence partition counts (every CTA
+    // builds its own copy: num_seqs <= 2048 integers)
+    if (warp == 0) {
+      int carry = 0;
+      for (int base = 0; base < p.num_seqs; base += 32) {
+        const int s = base + lane;
+        int n = 0;
+        if (s < p.num_seqs) {
+          const int c = p.context_lens[s];
+          n = c > 0 ? (c + part_tokens - 1) / part_tokens : 1;   // empty context: one item writes zeros
+        }
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (s < p.num_seqs) cum[s] = carry + incl - n;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) cum[p.num_seqs] = carry;
+    }
+    __syncthreads();
+    total_items = cum[p.num_seqs] * p.passes * p.num_kv_heads;
+  } else {
+    __syncwarp();
+    total_items = p.num_seqs * p.n_part * p.passes * p.num_kv_heads;
+  }
 
-  // lane geometry
+  // lane geometry (FMA path)
   const int k_tok = lane % BS, k_grp = lane / BS;       // q.k: token, chunk phase
-  const int v_row = lane / C::LPR, v_sub = lane % C::LPR;  // p.v: first row, token chunk
+  const int v_row = lane / (C::LPR > 0 ? C::LPR : 1), v_sub = lane % (C::LPR > 0 ? C::LPR : 1);
+  // lane geometry (MMA path): g = row of the 16 x 8 fragment, t4 = column pair
+  const int g = lane >> 2, t4 = lane & 3;
 
   int stage_c = 0;        // consumer cursor over the ring (continues across items)
   uint32_t phase_c = 0;
   int stage_p = 0;        // producer cursor
+  int inflight = 0;       // tiles issued and not yet consumed
 
   const float scale_l2 = p.scale * kLog2e;
-  const int total_warps = gridDim.x * (blockDim.x >> 5);
+  const int total_warps = gridDim.x * nwarps;
 
-  while (true) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&p.counters[0], 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= p.total_items) break;
-
-    // item -> (seq, part, pass, kvh), kvh fastest
-    int t = item;
-    const int kvh = t % p.num_kv_heads;
-    t /= p.num_kv_heads;
-    const int pass = t % p.passes;
-    t /= p.passes;
-    const int part = t % p.n_part;
-    const int seq = t / p.n_part;
-
-    const int ctx = p.context_lens[seq];
-    const int nblk_ctx = (ctx + BS - 1) / BS;
-    const int blk0 = part * p.part_blocks;
-    const int blk1 = min(blk0 + p.part_blocks, nblk_ctx);
-    const int ntiles = blk1 - blk0;
-    const int head0 = kvh * p.group + pass * GT;             // first q head of this pass
-    const int nheads = min(GT, p.group - pass * GT);          // live heads in this pass
-
-    if (ntiles <= 0) {
-      // empty context: the reference writes zeros (accs stay 0).  Empty partitions of a split
-      // launch are never read by the reduce step.
-      if (!p.split && part == 0) {
-        T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head0) * D;
-        for (int i = lane; i < nheads * D; i += 32) o[i] = ST<T>::from_f(0.f);
-      }
-      continue;
-    }
-
-    const int32_t* bt = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + blk0;
-    const char* kbase = reinterpret_cast<const char*>(p.k_cache) + (int64_t)kvh * p.kv_head_stride;
-    const char* vbase = reinterpret_cast<const char*>(p.v_cache) + (int64_t)kvh * p.kv_head_stride;
-
-    // block ids: lane i holds the id of tile (batch*32 + i); one coalesced load per 32 tiles
-    int bt_cur = lane < ntiles ? bt[lane] : 0;
-    int bt_next = 32 + lane < ntiles ? bt[32 + lane] : 0;
-
-    // stage q: [GT][D] as QS (zero rows for dead heads so their dot products stay finite)
-    {
-      const T* qg = reinterpret_cast<const T*>(p.q) + (int64_t)seq * p.q_stride + (int64_t)head0 * D;
-      for (int i = lane; i < GT * D; i += 32) {
-        const int h = i / D;
-        const float f = h < nheads ? ST<T>::to_f(qg[i]) : 0.f;
-        q_s[i] = to_qs<QS>(f);
-      }
-    }
-    __syncwarp();
-
-    // pipeline prologue: put up to S tiles in flight
-    const int npro = min(S, ntiles);
-    for (int i = 0; i < npro; ++i) {
-      const int bid = __shfl_sync(0xffffffffu, bt_cur, i & 31);  // S <= 32
+  // issue tiles of `it` while the ring has room
+  auto pump = [&](Item& it) {
+    if (!it.valid) return;
+    const char* kbase = reinterpret_cast<const char*>(p.k_cache) + (int64_t)it.kvh * p.kv_head_stride;
+    const char* vbase = reinterpret_cast<const char*>(p.v_cache) + (int64_t)it.kvh * p.kv_head_stride;
+    while (inflight < S && it.issued < it.ntiles) {
+      const int i = it.issued;
+      const int bid = __shfl_sync(0xffffffffu, i < 32 ? it.bt0 : it.bt1, i & 31);
       if (lane == 0) {
         const uint32_t bar = bars + 8 * stage_p;
         const uint32_t dst = tiles_s + stage_p * 2 * C::TILE_BYTES;
@@ -331,172 +451,378 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         bulk_g2s(dst + C::TILE_BYTES, vbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES, bar);
       }
       stage_p = stage_p + 1 == S ? 0 : stage_p + 1;
+      ++it.issued;
+      ++inflight;
+    }
+  };
+
+  Item cur, nxt;
+  claim(cur, p, cum, total_items, part_tokens, BS, lane);
+  pump(cur);
+  claim(nxt, p, cum, total_items, part_tokens, BS, lane);
+  pump(nxt);
+
+  while (cur.valid) {
+    const int seq = cur.seq, part = cur.part, kvh = cur.kvh, ctx = cur.ctx;
+    const int ntiles = cur.ntiles, blk0 = cur.blk0;
+    const int nblk_ctx = (ctx + BS - 1) / BS;
+    const int head0 = kvh * p.group + cur.pass * GT;             // first q head of this pass
+    const int nheads = min(GT, p.group - cur.pass * GT);          // live heads in this pass
+    const bool partial = p.always_partial || cur.nparts > 1;
+
+    if (ntiles <= 0) {
+      // empty context: the reference leaves zeros (its accumulators stay 0)
+      if (part == 0) {
+        T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head0) * D;
+        for (int i = lane; i < nheads * D; i += 32) o[i] = ST<T>::from_f(0.f);
+      }
+      cur = nxt;
+      claim(nxt, p, cum, total_items, part_tokens, BS, lane);
+      pump(cur);
+      pump(nxt);
+      continue;
     }
 
-    float m[GT], l[GT], acc[GT][C::RI], slope[GT];
+    // running softmax state.  FMA: per head, replicated over the lanes of a token / row.
+    // MMA: rows g (and g+8) of the 16-row tile, replicated over the 4 lanes of a row.
+    constexpr int NR = MMA ? (C::R16 ? 2 : 1) : GT;
+    float m[NR], l[NR], slope[NR];
+    float acc[MMA ? 1 : GT][MMA ? 1 : C::RI];
+    float o_acc[MMA ? C::ND : 1][4];
+    uint32_t qa[MMA ? C::KS : 1][4];
 #pragma unroll
-    for (int h = 0; h < GT; ++h) {
-      m[h] = -INFINITY;
-      l[h] = 0.f;
-      slope[h] = (p.alibi_slopes != nullptr && h < nheads) ? p.alibi_slopes[head0 + h] * kLog2e : 0.f;
+    for (int r = 0; r < NR; ++r) {
+      m[r] = -INFINITY;
+      l[r] = 0.f;
+      const int h = MMA ? g + 8 * r : r;
+      slope[r] = (p.alibi_slopes != nullptr && h < nheads) ? p.alibi_slopes[head0 + h] * kLog2e : 0.f;
+    }
+    if constexpr (MMA) {
 #pragma unroll
-      for (int i = 0; i < C::RI; ++i) acc[h][i] = 0.f;
+      for (int i = 0; i < C::ND; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+      // q fragments (A operand, 16 rows = query heads, k = head dim).  For e5m2 caches the k
+      // slots of a step are permuted so that a thread's four K bytes are contiguous:
+      // slots {2t,2t+1,2t+8,2t+9} <-> head-dim offsets {4t,4t+1,4t+2,4t+3}.
+      const T* qg = reinterpret_cast<const T*>(p.q) + (int64_t)seq * p.q_stride + (int64_t)head0 * D;
+#pragma unroll
+      for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int h = g + 8 * r;
+          uint32_t lo = 0, hi = 0;
+          if (h < nheads && (r == 0 || C::R16)) {
+            const T* src = qg + (int64_t)h * D + ks * 16;
+            if constexpr (C::FP8) {
+              const uint2 w = *reinterpret_cast<const uint2*>(src + 4 * t4);
+              if constexpr (std::is_same<T, __half>::value) {
+                lo = w.x;
+                hi = w.y;
+              } else {   // bf16 query, f16 tensor-core operands
+                const float2 a = unpack2<__nv_bfloat16>(w.x), b = unpack2<__nv_bfloat16>(w.y);
+                lo = pack2<__half>(a.x, a.y);
+                hi = pack2<__half>(b.x, b.y);
+              }
+            } else {
+              lo = *reinterpret_cast<const uint32_t*>(src + 2 * t4);
+              hi = *reinterpret_cast<const uint32_t*>(src + 8 + 2 * t4);
+            }
+          }
+          qa[ks][r] = lo;        // a0 (row g) / a1 (row g+8): k slots 2t, 2t+1
+          qa[ks][2 + r] = hi;    // a2 / a3: k slots 2t+8, 2t+9
+        }
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < GT; ++h)
+#pragma unroll
+        for (int i = 0; i < C::RI; ++i) acc[h][i] = 0.f;
+      // stage q: [GT][D] as QS (zero rows for dead heads so their dot products stay finite)
+      const T* qg = reinterpret_cast<const T*>(p.q) + (int64_t)seq * p.q_stride + (int64_t)head0 * D;
+      for (int i = lane; i < GT * D; i += 32) {
+        const int h = i / D;
+        const float f = h < nheads ? ST<T>::to_f(qg[i]) : 0.f;
+        q_s[i] = to_qs<QS>(f);
+      }
+      __syncwarp();
     }
 
     for (int tile = 0; tile < ntiles; ++tile) {
-      if (tile > 0 && (tile & 31) == 0) {  // advance the block-id window
-        bt_cur = bt_next;
-        const int nx = tile + 32 + lane;
-        bt_next = nx < ntiles ? bt[nx] : 0;
-      }
       const uint32_t ktile = tiles_s + stage_c * 2 * C::TILE_BYTES;
       const uint32_t vtile = ktile + C::TILE_BYTES;
       mbar_wait(bars + 8 * stage_c, phase_c);
+      const int tok0 = (blk0 + tile) * BS;
+      const bool last_partial = (blk0 + tile == nblk_ctx - 1) && (ctx % BS != 0);
 
-      // ---- s = q.k for this lane's token --------------------------------------------------------
-      float s[GT];
+      if constexpr (MMA) {
+        // ---- tensor-core path -------------------------------------------------------------------
+        if (last_partial) {
+          // zero the out-of-context columns of the V tile (they may hold NaNs, p = 0 there)
+          const int valid = ctx - tok0;
+          unsigned char* vt = wbase + (size_t)stage_c * 2 * C::TILE_BYTES + C::TILE_BYTES;
+          for (int i = lane; i < D * BS; i += 32)
+            if (i % BS >= valid) reinterpret_cast<CT*>(vt)[i] = CT(0);
+          // these generic-proxy writes must be ordered before the TMA refill of this stage
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+        }
+        float s[C::NT][4];
 #pragma unroll
-      for (int h = 0; h < GT; ++h) s[h] = 0.f;
+        for (int nt = 0; nt < C::NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if constexpr (!C::FP8) {
+          // K tile [D/8][BS][8]: chunk c, tokens 8nt..8nt+7 is one 8x8 b16 matrix (rows 16 B apart)
 #pragma unroll
-      for (int j = 0; j < C::KJ; ++j) {
-        const int c = k_grp + j * C::TG;
-        if (C::NCH % C::TG == 0 || c < C::NCH) {
-          const uint4 kv = lds16(ktile + (c * BS + k_tok) * 16);
+          for (int ks = 0; ks < C::KS; ++ks) {
+            if constexpr (C::NT >= 2) {
 #pragma unroll
-          for (int h = 0; h < GT; ++h) {
-            uint4 qw[C::QW];
+              for (int np = 0; np < C::NT / 2; ++np) {
+                uint32_t b[4];
+                const int j = lane >> 3;
+                ldsm_x4(ktile + (((2 * ks + (j & 1)) * BS + 16 * np + 8 * (j >> 1) + (lane & 7)) << 4), b);
+                mma16816<MT>(s[2 * np], qa[ks], b[0], b[1]);
+                mma16816<MT>(s[2 * np + 1], qa[ks], b[2], b[3]);
+              }
+            } else {   // BS == 8: one n-tile; matrices 2,3 of the x4 load are ignored duplicates
+              uint32_t b[4];
+              const int j = (lane >> 3) & 1;
+              ldsm_x4(ktile + (((2 * ks + j) * BS + (lane & 7)) << 4), b);
+              mma16816<MT>(s[0], qa[ks], b[0], b[1]);
+            }
+          }
+        } else {
+          // e5m2 K tile [D/16][BS][16]: thread (g, t4) reads bytes 4t4..4t4+3 of token n = 8nt+g
 #pragma unroll
-            for (int w = 0; w < C::QW; ++w)
-              qw[w] = lds16(q_sa + (h * D + c * C::EPC) * (int)sizeof(QS) + w * 16);
-            s[h] = dot_chunk<T, C>(s[h], kv, qw);
+          for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < C::NT; ++nt) {
+              const uint32_t w = lds4(ktile + ((ks * BS + 8 * nt + g) << 4) + 4 * t4);
+              mma16816<MT>(s[nt], qa[ks], __byte_perm(w, 0, 0x1404), __byte_perm(w, 0, 0x3424));
+            }
           }
         }
-      }
+        // ---- online softmax on the fragments (log2 domain) --------------------------------------
+        uint32_t pa[C::KT][4];
 #pragma unroll
-      for (int h = 0; h < GT; ++h) {
+        for (int kt = 0; kt < C::KT; ++kt) pa[kt][0] = pa[kt][1] = pa[kt][2] = pa[kt][3] = 0u;
 #pragma unroll
-        for (int o = BS; o < 32; o <<= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
-      }
-
-      // ---- online softmax (log2 domain) ---------------------------------------------------------
-      const int tok = (blk0 + tile) * BS + k_tok;
-      const bool valid = tok < ctx;
+        for (int r = 0; r < NR; ++r) {
+          float mx = -INFINITY;
 #pragma unroll
-      for (int h = 0; h < GT; ++h) {
-        float sv = s[h] * scale_l2 + slope[h] * (float)(tok - ctx + 1);
-        sv = valid ? sv : -INFINITY;
-        float mx = sv;
+          for (int nt = 0; nt < C::NT; ++nt) {
 #pragma unroll
-        for (int o = 1; o < BS; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const float m_new = fmaxf(m[h], mx);
-        const QS pq = to_qs<QS>(exp2f(sv - m_new));
-        if (k_grp == 0) p_s[h * BS + k_tok] = pq;
-        if (m_new > m[h]) {  // warp-uniform
-          const float alpha = exp2f(m[h] - m_new);
-          l[h] *= alpha;
+            for (int e = 0; e < 2; ++e) {
+              const int tok = tok0 + 8 * nt + 2 * t4 + e;
+              float sv = s[nt][2 * r + e] * scale_l2 + slope[r] * (float)(tok - ctx + 1);
+              sv = tok < ctx ? sv : -INFINITY;
+              s[nt][2 * r + e] = sv;
+              mx = fmaxf(mx, sv);
+            }
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float m_new = fmaxf(m[r], mx);    // finite: a scheduled tile has a valid token
+          const float alpha = exp2f(m[r] - m_new);
+          m[r] = m_new;
+          l[r] *= alpha;
 #pragma unroll
-          for (int i = 0; i < C::RI; ++i) acc[h][i] *= alpha;
-          m[h] = m_new;
+          for (int i = 0; i < C::ND; ++i) {
+            o_acc[i][2 * r] *= alpha;
+            o_acc[i][2 * r + 1] *= alpha;
+          }
+#pragma unroll
+          for (int nt = 0; nt < C::NT; ++nt) {
+            const uint32_t pk = pack2<MT>(exp2f(s[nt][2 * r] - m_new), exp2f(s[nt][2 * r + 1] - m_new));
+            const float2 pf = unpack2<MT>(pk);
+            l[r] += pf.x + pf.y;                   // the sum uses the rounded p, like the weights
+            pa[nt >> 1][(nt & 1) * 2 + r] = pk;    // a0/a1: tokens 16kt+2t.. ; a2/a3: +8
+          }
         }
-        l[h] += qs_to_f<QS>(pq);
-      }
-      __syncwarp();
-
-      // ---- acc += p.v ---------------------------------------------------------------------------
-      const bool last_partial = (blk0 + tile == nblk_ctx - 1) && (ctx % BS != 0);
-      const int vvalid = ctx - (blk0 + tile) * BS - v_sub * C::EPC;  // valid tokens in my chunk
-      uint4 pw[C::P_IN_REGS ? GT : 1][C::QW];
-      if constexpr (C::P_IN_REGS) {
+        // ---- o += p.v ---------------------------------------------------------------------------
+        if constexpr (!C::FP8) {
+          // V tile [D][BS]: rows 8nd..8nd+7, tokens 16kt+8h..+7 is one 8x8 matrix (rows 2*BS B apart)
 #pragma unroll
-        for (int h = 0; h < GT; ++h)
+          for (int kt = 0; kt < C::KT; ++kt) {
 #pragma unroll
-          for (int w = 0; w < C::QW; ++w)
-            pw[h][w] = lds16(p_sa + (h * BS + v_sub * C::EPC) * (int)sizeof(QS) + w * 16);
-      }
+            for (int nd = 0; nd < C::ND; nd += 2) {
+              uint32_t b[4];
+              const int j = lane >> 3;
+              if constexpr (BS >= 16) {
+                ldsm_x4(vtile + ((8 * (nd + (j >> 1)) + (lane & 7)) * BS + 16 * kt + 8 * (j & 1)) * 2, b);
+                mma16816<MT>(o_acc[nd], pa[kt], b[0], b[1]);
+                mma16816<MT>(o_acc[nd + 1], pa[kt], b[2], b[3]);
+              } else {   // BS == 8: tokens 8..15 of the k-step do not exist (p = 0 there)
+                ldsm_x4(vtile + ((8 * (nd + (j >> 1)) + (lane & 7)) * BS) * 2, b);
+                mma16816<MT>(o_acc[nd], pa[kt], b[0], 0u);
+                mma16816<MT>(o_acc[nd + 1], pa[kt], b[2], 0u);
+              }
+            }
+          }
+        } else {
+          // e5m2 V tile [D][BS] bytes.  p's k slots are tokens 16kt + {2t,2t+1,8+2t,9+2t}: two
+          // 16-bit loads per (row, k-step)
 #pragma unroll
-      for (int i = 0; i < C::RI; ++i) {
-        const int row = v_row + i * C::RPI;
-        if (D % C::RPI == 0 || row < D) {
-          uint4 vv = lds16(vtile + (row * C::LPR + v_sub) * 16);
-          if (last_partial) mask_chunk<C>(vv, vvalid);
+          for (int kt = 0; kt < C::KT; ++kt) {
 #pragma unroll
-          for (int h = 0; h < GT; ++h) {
-            if constexpr (C::P_IN_REGS) {
-              acc[h][i] = dot_chunk<T, C>(acc[h][i], vv, pw[h]);
-            } else {
-              uint4 pl[C::QW];
+            for (int nd = 0; nd < C::ND; ++nd) {
+              const uint32_t row = vtile + (8 * nd + g) * BS + 16 * kt;
+              uint32_t w0, w1 = 0;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w0) : "r"(row + 2 * t4));
+              if constexpr (BS >= 16)
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w1) : "r"(row + 8 + 2 * t4));
+              mma16816<MT>(o_acc[nd], pa[kt], __byte_perm(w0, 0, 0x1404), __byte_perm(w1, 0, 0x1404));
+            }
+          }
+        }
+      } else {
+        // ---- FMA path: s = q.k for this lane's token ---------------------------------------------
+        float s[GT];
+#pragma unroll
+        for (int h = 0; h < GT; ++h) s[h] = 0.f;
+#pragma unroll
+        for (int j = 0; j < C::KJ; ++j) {
+          const int c = k_grp + j * C::TG;
+          if (C::NCH % C::TG == 0 || c < C::NCH) {
+            const uint4 kv = lds16(ktile + (c * BS + k_tok) * 16);
+#pragma unroll
+            for (int h = 0; h < GT; ++h) {
+              uint4 qw[C::QW];
 #pragma unroll
               for (int w = 0; w < C::QW; ++w)
-                pl[w] = lds16(p_sa + (h * BS + v_sub * C::EPC) * (int)sizeof(QS) + w * 16);
-              acc[h][i] = dot_chunk<T, C>(acc[h][i], vv, pl);
+                qw[w] = lds16(q_sa + (h * D + c * C::EPC) * (int)sizeof(QS) + w * 16);
+              s[h] = dot_chunk<T, C>(s[h], kv, qw);
+            }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < GT; ++h) {
+#pragma unroll
+          for (int o = BS; o < 32; o <<= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+        }
+        // online softmax (log2 domain)
+        const int tok = tok0 + k_tok;
+        const bool valid = tok < ctx;
+#pragma unroll
+        for (int h = 0; h < GT; ++h) {
+          float sv = s[h] * scale_l2 + slope[h] * (float)(tok - ctx + 1);
+          sv = valid ? sv : -INFINITY;
+          float mx = sv;
+#pragma unroll
+          for (int o = 1; o < BS; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          const float m_new = fmaxf(m[h], mx);
+          const QS pq = to_qs<QS>(exp2f(sv - m_new));
+          if (k_grp == 0) p_s[h * BS + k_tok] = pq;
+          if (m_new > m[h]) {  // warp-uniform
+            const float alpha = exp2f(m[h] - m_new);
+            l[h] *= alpha;
+#pragma unroll
+            for (int i = 0; i < C::RI; ++i) acc[h][i] *= alpha;
+            m[h] = m_new;
+          }
+          l[h] += qs_to_f<QS>(pq);
+        }
+        __syncwarp();
+        // acc += p.v
+        const int vvalid = ctx - tok0 - v_sub * C::EPC;  // valid tokens in my chunk
+        uint4 pw[C::P_IN_REGS ? GT : 1][C::QW];
+        if constexpr (C::P_IN_REGS) {
+#pragma unroll
+          for (int h = 0; h < GT; ++h)
+#pragma unroll
+            for (int w = 0; w < C::QW; ++w)
+              pw[h][w] = lds16(p_sa + (h * BS + v_sub * C::EPC) * (int)sizeof(QS) + w * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < C::RI; ++i) {
+          const int row = v_row + i * C::RPI;
+          if (D % C::RPI == 0 || row < D) {
+            uint4 vv = lds16(vtile + (row * C::LPR + v_sub) * 16);
+            if (last_partial) mask_chunk<C>(vv, vvalid);
+#pragma unroll
+            for (int h = 0; h < GT; ++h) {
+              if constexpr (C::P_IN_REGS) {
+                acc[h][i] = dot_chunk<T, C>(acc[h][i], vv, pw[h]);
+              } else {
+                uint4 pl[C::QW];
+#pragma unroll
+                for (int w = 0; w < C::QW; ++w)
+                  pl[w] = lds16(p_sa + (h * BS + v_sub * C::EPC) * (int)sizeof(QS) + w * 16);
+                acc[h][i] = dot_chunk<T, C>(acc[h][i], vv, pl);
+              }
             }
           }
         }
       }
       __syncwarp();  // every lane is done with this stage (and with p_s)
-
-      // ---- refill the stage just freed ----------------------------------------------------------
-      const int nt = tile + S;
-      if (nt < ntiles) {
-        const int src = ((nt >> 5) == (tile >> 5)) ? bt_cur : bt_next;
-        const int bid = __shfl_sync(0xffffffffu, src, nt & 31);
-        if (lane == 0) {
-          const uint32_t bar = bars + 8 * stage_p;
-          const uint32_t dst = tiles_s + stage_p * 2 * C::TILE_BYTES;
-          mbar_expect_tx(bar, 2 * C::TILE_BYTES);
-          bulk_g2s(dst, kbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES, bar);
-          bulk_g2s(dst + C::TILE_BYTES, vbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES,
-                   bar);
-        }
-        stage_p = stage_p + 1 == S ? 0 : stage_p + 1;
-      }
+      --inflight;
       if (++stage_c == S) {
         stage_c = 0;
         phase_c ^= 1;
       }
+      // refill the freed stage: this item first, then the next one (lookahead across items)
+      pump(cur);
+      pump(nxt);
     }
 
-    // ---- epilogue: finish the reductions, normalise, store -------------------------------------
+    // ---- epilogue: finish the reductions, normalise, store / publish the partial ----------------
+    // Layout-independent description of what this lane owns: FMA: head h, rows v_row + i*RPI
+    // (lanes v_sub == 0); MMA: rows g (+8), columns 8nd + 2t4 + {0,1}.
+    if constexpr (MMA) {
 #pragma unroll
-    for (int h = 0; h < GT; ++h) {
-      float lt = l[h];
+      for (int r = 0; r < NR; ++r) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+      }
+    } else {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) lt += __shfl_xor_sync(0xffffffffu, lt, o);
-      l[h] = lt * (1.0f / C::TG);  // every token was counted by its TG lanes
+      for (int h = 0; h < GT; ++h) {
+        float lt = l[h];
 #pragma unroll
-      for (int i = 0; i < C::RI; ++i) {
-        float a = acc[h][i];
+        for (int o = 1; o < 32; o <<= 1) lt += __shfl_xor_sync(0xffffffffu, lt, o);
+        l[h] = lt * (1.0f / C::TG);  // every token was counted by its TG lanes
 #pragma unroll
-        for (int o = 1; o < C::LPR; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        acc[h][i] = a;
+        for (int i = 0; i < C::RI; ++i) {
+          float a = acc[h][i];
+#pragma unroll
+          for (int o = 1; o < C::LPR; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          acc[h][i] = a;
+        }
       }
     }
 #pragma unroll
-    for (int h = 0; h < GT; ++h) {
+    for (int r = 0; r < NR; ++r) {
+      const int h = MMA ? g + 8 * r : r;
       if (h < nheads) {
         const int head = head0 + h;
-        const float inv = __fdividef(1.f, l[h] + 1e-6f);
-        if (!p.split) {
-          T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head) * D;
-          if (v_sub == 0) {
+        const float inv = __fdividef(1.f, l[r] + 1e-6f);
+        const int64_t pi = ((int64_t)seq * p.num_heads + head) * p.n_part + part;
+        if (partial && (MMA ? t4 == 0 : lane == 0)) {
+          p.max_logits[pi] = m[r] * kLn2;  // natural-log domain, as the reference stores qk_max
+          p.exp_sums[pi] = l[r];
+        }
+        T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head) * D;
+        const bool direct = cur.nparts == 1;   // single partition: the result is final
+        if constexpr (MMA) {
 #pragma unroll
-            for (int i = 0; i < C::RI; ++i) {
-              const int row = v_row + i * C::RPI;
-              if (D % C::RPI == 0 || row < D) o[row] = ST<T>::from_f(acc[h][i] * inv);
+          for (int nd = 0; nd < C::ND; ++nd) {
+            const int col = 8 * nd + 2 * t4;
+            const float v0 = o_acc[nd][2 * r] * inv, v1 = o_acc[nd][2 * r + 1] * inv;
+            if (direct) *reinterpret_cast<uint32_t*>(o + col) = pack2<T>(v0, v1);
+            if (partial) {
+              if (p.tmp_is_f32)
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.tmp_out) + pi * D + col) =
+                    make_float2(v0, v1);
+              else
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.tmp_out) + pi * D + col) =
+                    pack2<T>(v0, v1);
             }
           }
-        } else {
-          const int64_t pi = ((int64_t)seq * p.num_heads + head) * p.n_part + part;
-          if (lane == 0) {
-            p.max_logits[pi] = m[h] * kLn2;  // natural-log domain, as the reference stores qk_max
-            p.exp_sums[pi] = l[h];
-          }
-          if (v_sub == 0) {
+        } else if (v_sub == 0) {
 #pragma unroll
-            for (int i = 0; i < C::RI; ++i) {
-              const int row = v_row + i * C::RPI;
-              if (D % C::RPI == 0 || row < D) {
-                const float v = acc[h][i] * inv;
+          for (int i = 0; i < C::RI; ++i) {
+            const int row = v_row + i * C::RPI;
+            if (D % C::RPI == 0 || row < D) {
+              const float v = acc[r][i] * inv;
+              if (direct) o[row] = ST<T>::from_f(v);
+              if (partial) {
                 if (p.tmp_is_f32)
                   reinterpret_cast<float*>(p.tmp_out)[pi * D + row] = v;
                 else
@@ -507,7 +833,66 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         }
       }
     }
+
+    // ---- merge: the warp that publishes a sequence's LAST partition combines them all ------------
+    // (reference: paged_attention_v2_reduce_kernel, :511-602: weights exp_sum_j*exp(max_j-max) /
+    // (sum + 1e-6) over per-partition normalised outputs)
+    if (cur.nparts > 1) {
+      __threadfence();
+      __syncwarp();
+      const int gid = (seq * p.passes + cur.pass) * p.num_kv_heads + kvh;
+      int done = 0;
+      if (lane == 0) done = atomicAdd(&p.tickets[gid], 1);
+      done = __shfl_sync(0xffffffffu, done, 0);
+      if (done == cur.nparts - 1) {
+        __threadfence();
+        const int np = cur.nparts;
+        for (int h = 0; h < nheads; ++h) {
+          const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
+          float mx = -INFINITY;
+          for (int j = lane; j < np; j += 32) mx = fmaxf(mx, __ldcg(p.max_logits + base + j));
+#pragma unroll
+          for (int o2 = 16; o2 >= 1; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+          float sum = 0.f;
+          for (int j = lane; j < np; j += 32)
+            sum += __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - mx);
+#pragma unroll
+          for (int o2 = 16; o2 >= 1; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
+          const float inv = __fdividef(1.0f, sum + 1e-6f);
+          float a[(D + 31) / 32];
+#pragma unroll
+          for (int i = 0; i < (D + 31) / 32; ++i) a[i] = 0.f;
+          for (int j = 0; j < np; ++j) {
+            const float w = __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - mx) * inv;
+#pragma unroll
+            for (int i = 0; i < (D + 31) / 32; ++i) {
+              const int d = lane + 32 * i;
+              if (D % 32 == 0 || d < D) {
+                float v;
+                if (p.tmp_is_f32)
+                  v = __ldcg(reinterpret_cast<const float*>(p.tmp_out) + (base + j) * D + d);
+                else
+                  v = load_cg_f<T>(reinterpret_cast<const T*>(p.tmp_out) + (base + j) * D + d);
+                a[i] += v * w;
+              }
+            }
+          }
+          T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head0 + h) * D;
+#pragma unroll
+          for (int i = 0; i < (D + 31) / 32; ++i) {
+            const int d = lane + 32 * i;
+            if (D % 32 == 0 || d < D) o[d] = ST<T>::from_f(a[i]);
+          }
+        }
+        if (lane == 0) p.tickets[gid] = 0;   // leave the ticket table clean for the next launch
+      }
+    }
     __syncwarp();  // q_s / p_s are rewritten by the next item
+
+    cur = nxt;
+    claim(nxt, p, cum, total_items, part_tokens, BS, lane);
+    pump(cur);
+    pump(nxt);
   }
 
   // self-resetting queue: the last warp to leave zeroes the counters for the next launch
@@ -518,64 +903,6 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       p.counters[1] = 0;
       __threadfence();
     }
-  }
-}
-
-// ---- merge of partitions (reference: paged_attention_v2_reduce_kernel, :511-602) -----------------
-// one warp per (seq, head); partial outputs are normalised per partition, weights are
-// exp_sum_j * exp(max_j - max) / (sum + 1e-6)
-template <typename T, typename PT, int D>
-__global__ void __launch_bounds__(128)
-    paged_attention_reduce_kernel(T* __restrict__ out, const float* __restrict__ exp_sums,
-                                  const float* __restrict__ max_logits,
-                                  const PT* __restrict__ tmp_out,
-                                  const int32_t* __restrict__ context_lens, int num_heads,
-                                  int n_part, int part_tokens, int total) {
-  const int lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // seq * num_heads + head
-  if (idx >= total) return;
-  const int seq = idx / num_heads;
-  const int ctx = context_lens[seq];
-  int np = (ctx + part_tokens - 1) / part_tokens;
-  np = np < n_part ? np : n_part;
-  T* o = out + (int64_t)idx * D;
-  if (np <= 0) {  // empty context
-    for (int i = lane; i < D; i += 32) o[i] = ST<T>::from_f(0.f);
-    return;
-  }
-  const float* ml = max_logits + (int64_t)idx * n_part;
-  const float* es = exp_sums + (int64_t)idx * n_part;
-  const PT* tp = tmp_out + (int64_t)idx * n_part * D;
-  if (np == 1) {  // nothing to merge: copy (reference :523-533)
-    for (int i = lane; i < D; i += 32) {
-      if constexpr (std::is_same<PT, float>::value)
-        o[i] = ST<T>::from_f(tp[i]);
-      else
-        o[i] = ST<T>::from_f(ST<PT>::to_f(tp[i]));
-    }
-    return;
-  }
-  float mx = -INFINITY;
-  for (int j = lane; j < np; j += 32) mx = fmaxf(mx, ml[j]);
-#pragma unroll
-  for (int o2 = 16; o2 >= 1; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-  float sum = 0.f;
-  for (int j = lane; j < np; j += 32) sum += es[j] * expf(ml[j] - mx);
-#pragma unroll
-  for (int o2 = 16; o2 >= 1; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
-  const float inv = __fdividef(1.0f, sum + 1e-6f);
-  for (int i = lane; i < D; i += 32) {
-    float a = 0.f;
-    for (int j = 0; j < np; ++j) {
-      const float w = es[j] * expf(ml[j] - mx) * inv;
-      float v;
-      if constexpr (std::is_same<PT, float>::value)
-        v = tp[(int64_t)j * D + i];
-      else
-        v = ST<PT>::to_f(tp[(int64_t)j * D + i]);
-      a += v * w;
-    }
-    o[i] = ST<T>::from_f(a);
   }
 }
 

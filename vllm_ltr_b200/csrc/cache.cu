@@ -9,9 +9,10 @@
 //   value_cache [num_blocks, num_kv_heads, head_size, block_size]
 //
 // B200 shape:
-//   reshape_and_cache — (token, head, 16-byte chunk) items flattened over the grid; the source is
-//     read with 128-bit loads, each K chunk is ONE 16-byte store (the layout keeps x elements of a
-//     token together), V is x scalar stores (the layout strides tokens by block_size).
+//   reshape_and_cache — one warp per (token, head) row flattened over the grid; each K chunk is
+//     read with 128-bit loads and written with ONE 16-byte store (the layout keeps x elements of
+//     a token together), V is scalar stores with lanes on consecutive head elements (the layout
+//     strides a token's elements by block_size: one 32-byte sector per element).
 //   copy_blocks — layer pointers and (src,dst) pairs travel as kernel parameters (CUDA >= 12.1
 //     allows 32 KB of them): no pointer-array tensors, no blocking H2D copies (the reference does
 //     three per call, cache_kernels.cu:129-136), 128-bit copies, grid sized over
@@ -34,47 +35,51 @@ __device__ __forceinline__ CT cache_cvt(T v) {
     return v;
 }
 
-// vector path: one thread moves XE = 16/sizeof(CT) consecutive head elements of one token
+// vector path: one warp per (token, head) row.
+//   K: the layout keeps x = XE consecutive head elements of a token together, so lane c moves
+//      chunk c with 128-bit loads and ONE 128-bit store.
+//   V: the layout strides a token's elements by block_size, every element lands in its own
+//      32-byte sector (read-modify-write in DRAM - inherent to the layout).  Lanes take
+//      CONSECUTIVE head elements, so one store instruction touches 32 sectors that are
+//      block_size*sizeof(CT) bytes apart (8 or fewer 128-byte lines) instead of 32 lines.
 template <typename T, typename CT, bool FP8>
 __global__ void __launch_bounds__(256)
     reshape_and_cache_vec_kernel(const T* __restrict__ key, const T* __restrict__ value,
                                  CT* __restrict__ key_cache, CT* __restrict__ value_cache,
                                  const int64_t* __restrict__ slot_mapping, int64_t key_stride,
                                  int64_t value_stride, int num_heads, int head_size,
-                                 int block_size, int64_t num_items) {
+                                 int block_size, int64_t num_rows) {
   constexpr int XE = 16 / sizeof(CT);              // == x
-  constexpr int LD = XE * sizeof(T) / 16;          // 16-byte loads per tensor per thread
+  constexpr int LD = XE * sizeof(T) / 16;          // 16-byte loads per K chunk
   constexpr int N = 16 / sizeof(T);
-  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= num_items) return;
-  const int chunks = head_size / XE;
-  const int chunk = (int)(item % chunks);
-  const int64_t th = item / chunks;
-  const int head = (int)(th % num_heads);
-  const int64_t token = th / num_heads;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= num_rows) return;
+  const int head = (int)(row % num_heads);
+  const int64_t token = row / num_heads;
   const int64_t slot = slot_mapping[token];
   if (slot < 0) return;  // padding token (cache_kernels.cu:172-175)
   const int64_t blk = slot / block_size;
   const int off = (int)(slot % block_size);
-
-  const T* ksrc = key + token * key_stride + (int64_t)head * head_size + chunk * XE;
-  const T* vsrc = value + token * value_stride + (int64_t)head * head_size + chunk * XE;
-  alignas(16) T kbuf[XE];
-  alignas(16) T vbuf[XE];
-#pragma unroll
-  for (int l = 0; l < LD; ++l) {
-    *reinterpret_cast<uint4*>(&kbuf[l * N]) = ld_nc_16(ksrc + l * N);
-    *reinterpret_cast<uint4*>(&vbuf[l * N]) = ld_nc_16(vsrc + l * N);
-  }
-  alignas(16) CT kout[XE];
-#pragma unroll
-  for (int e = 0; e < XE; ++e) kout[e] = cache_cvt<T, CT, FP8>(kbuf[e]);
+  const int chunks = head_size / XE;
   const int64_t bh = blk * num_heads + head;
-  CT* kdst = key_cache + ((bh * chunks + chunk) * block_size + off) * XE;
-  st_16(kdst, *reinterpret_cast<uint4*>(kout));
-  CT* vdst = value_cache + (bh * head_size + chunk * XE) * block_size + off;
+  const T* ksrc = key + token * key_stride + (int64_t)head * head_size;
+  const T* vsrc = value + token * value_stride + (int64_t)head * head_size;
+  // V first: its scattered stores are the long pole, get them in flight early
+  CT* vdst = value_cache + bh * head_size * block_size + off;
+  for (int d = lane; d < head_size; d += 32)
+    vdst[(int64_t)d * block_size] = cache_cvt<T, CT, FP8>(vsrc[d]);
+  for (int chunk = lane; chunk < chunks; chunk += 32) {
+    alignas(16) T kbuf[XE];
 #pragma unroll
-  for (int e = 0; e < XE; ++e) vdst[(int64_t)e * block_size] = cache_cvt<T, CT, FP8>(vbuf[e]);
+    for (int l = 0; l < LD; ++l)
+      *reinterpret_cast<uint4*>(&kbuf[l * N]) = ld_nc_16(ksrc + chunk * XE + l * N);
+    alignas(16) CT kout[XE];
+#pragma unroll
+    for (int e = 0; e < XE; ++e) kout[e] = cache_cvt<T, CT, FP8>(kbuf[e]);
+    CT* kdst = key_cache + ((bh * chunks + chunk) * block_size + off) * XE;
+    st_16(kdst, *reinterpret_cast<uint4*>(kout));
+  }
 }
 
 // scalar path: one element per thread, any x / alignment
@@ -115,10 +120,10 @@ int launch_reshape(const void* key, const void* value, void* key_cache, void* va
                       value_stride % N == 0 && (uintptr_t)key % 16 == 0 &&
                       (uintptr_t)value % 16 == 0 && (uintptr_t)key_cache % 16 == 0;
   if (vec_ok) {
-    const int64_t items = (int64_t)num_tokens * num_heads * (head_size / XE);
-    reshape_and_cache_vec_kernel<T, CT, FP8><<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
+    const int64_t rows = (int64_t)num_tokens * num_heads;
+    reshape_and_cache_vec_kernel<T, CT, FP8><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
         (const T*)key, (const T*)value, (CT*)key_cache, (CT*)value_cache, slot_mapping,
-        key_stride, value_stride, num_heads, head_size, block_size, items);
+        key_stride, value_stride, num_heads, head_size, block_size, rows);
   } else {
     const int64_t items = (int64_t)num_tokens * num_heads * head_size;
     reshape_and_cache_scalar_kernel<T, CT, FP8>

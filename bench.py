@@ -96,6 +96,65 @@ def step_bytes(ctx, shape, block_size, layers):
 
 
 # ---------------------------------------------------------------------------------------------
+# the LTR scheduling tick that runs once per engine step
+# ---------------------------------------------------------------------------------------------
+def tick_workload(n_live: int, prompt_len: int, seed: int = 0):
+    """fp16-quantised scores of the live requests (what logits[:,0].tolist() yields) and the
+    token ids of the prompt that arrives this step (steady state of the trace: completions per
+    step ~ B / mean output length < 1, so one new prompt of the trace's mean length per step)."""
+    rng = np.random.default_rng(seed + 7)
+    scores = rng.normal(0, 1, n_live).astype(np.float16).astype(np.float64)
+    prompt = rng.integers(1000, 49000, prompt_len).tolist()
+    return scores, prompt
+
+
+class GpuTick:
+    """a8 + a10 on a side stream: score the newly arrived prompt with the OPT-125M predictor and
+    order all live requests by score; the scheduler thread waits only on that stream."""
+
+    def __init__(self, dev, n_live, prompt_len):
+        from vllm_ltr_b200.ltr_scheduler import GpuRanker
+        from vllm_ltr_b200.predictor import OPTPredictor, dummy_checkpoint
+        self.scores, self.prompt = tick_workload(n_live, prompt_len)
+        cfg, sd = dummy_checkpoint("125m", seed=0)
+        self.pred = OPTPredictor(cfg, sd, device=dev)
+        self.ranker = GpuRanker()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.last = None
+
+    def __call__(self):
+        with torch.cuda.stream(self.stream):
+            s = self.pred.scores([self.prompt])          # D2H of the score: syncs the side stream
+            self.scores[0] = s[0]
+            self.last = self.ranker.order(self.scores)   # H2D keys, rank kernel, D2H permutation
+        return self.last
+
+
+class CpuTick:
+    """The same tick the way the reference does it on the host: Python's sorted over the live
+    requests (scheduler.py:998) and an fp32 forward of the predictor architecture (HF
+    OPTForSequenceClassification, the class train/trainer.py saves) on the host cores."""
+
+    def __init__(self, n_live, prompt_len):
+        import transformers
+        self.scores, self.prompt = tick_workload(n_live, prompt_len)
+        cfg = transformers.OPTConfig(hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                                     ffn_dim=3072, word_embed_proj_dim=768, vocab_size=50272,
+                                     max_position_embeddings=2048, num_labels=1,
+                                     do_layer_norm_before=True)
+        torch.manual_seed(0)
+        self.model = transformers.OPTForSequenceClassification(cfg).eval()
+        self.ids = torch.tensor([self.prompt])
+
+    def __call__(self):
+        with torch.no_grad():
+            s = float(self.model(input_ids=self.ids).logits[0, 0].to(torch.float16))
+        sc = self.scores.tolist()
+        sc[0] = s
+        return sorted(range(len(sc)), key=lambda i: -sc[i])
+
+
+# ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -238,22 +297,35 @@ def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_bat
     hidden = torch.randn(len(sctx), cshape.hidden).to(cshape.dtype)
     mx = int(sctx.max())
 
+    tick = CpuTick(args.live_requests, args.tick_prompt_len) if args.tick else None
+
     def one():
         hp.step(hidden, inp["positions"], inp["slot_mapping"], inp["block_tables"],
                 inp["context_lens"], mx)
 
     for _ in range(warmup):
         one()
+        if tick:
+            tick()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
     dt = (time.perf_counter() - t0) / steps
-    full = dt * shape.layers / sample_layers
+    tick_s = 0.0
+    if tick:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tick()
+        tick_s = (time.perf_counter() - t0) / steps
+    full = dt * shape.layers / sample_layers + tick_s
     tps = len(sctx) / full
     desc = (f"{len(sctx)} of {len(ctx)} sequences of the trace x {sample_layers} of {shape.layers} "
             f"layers per step, time scaled by {shape.layers}/{sample_layers}; "
             f"csrc/cpu kernels ({'oracle/_ref' if kind == 'reference' else 'oracle port'}), "
-            f"{str(cshape.dtype).split('.')[-1]}, OMP threads={cores}")
+            f"{str(cshape.dtype).split('.')[-1]}, OMP threads={cores}"
+            + (f"; + LTR tick per step ({tick_s * 1e3:.1f} ms: Python sorted over "
+               f"{args.live_requests} live requests + HF OPT-125M fp32 forward of one "
+               f"{args.tick_prompt_len}-token prompt)" if tick else ""))
     return tps, full * 1e3, desc, cores, kind
 
 
@@ -270,6 +342,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--cpu-sample-batch", type=int, default=256)
+    ap.add_argument("--no-tick", dest="tick", action="store_false",
+                    help="leave the LTR scheduling tick (a8, a10) out of the step")
+    ap.add_argument("--live-requests", type=int, default=10000,
+                    help="live requests ordered per tick (synthetic-sharegpt.sh submits 10000)")
+    ap.add_argument("--tick-prompt-len", type=int, default=245)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -289,7 +366,10 @@ def main():
     workload = (f"{args.model} decode hot path (a1-a7: rms_norm/fused_add_rms_norm, rotary, "
                 f"reshape_and_cache, paged_attention, silu_and_mul x {bench_shape.layers} layers; "
                 f"GEMMs excluded), B={args.batch} running sequences of the synthetic ShareGPT "
-                f"trace (contexts mean {ctx.mean():.0f}, max {ctx.max()}), block 16")
+                f"trace (contexts mean {ctx.mean():.0f}, max {ctx.max()}), block 16"
+                + (f"; + LTR tick per step (a8 rank of {args.live_requests} live requests, a10 "
+                   f"OPT-125M predictor forward of one {args.tick_prompt_len}-token prompt)"
+                   if args.tick else ""))
     config = {"workload": workload, "batch": args.batch, "layers": bench_shape.layers,
               "sum_context_tokens": int(ctx.sum()), "parallelism": f"tp{world}",
               "l2": "inputs larger than L2 (each layer reads its own KV pool)"}
@@ -340,11 +420,18 @@ def main():
         from vllm_ltr_b200.parallel import tensor_model_parallel_all_reduce
         all_reduce = tensor_model_parallel_all_reduce
 
+    # the scheduler (and with it the tick) lives on the driver rank only
+    tick = GpuTick(dev, args.live_requests, args.tick_prompt_len) if (args.tick and rank == 0) else None
+
     def step_resident():
+        if tick:
+            tick()
         return hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
                        devin["block_tables"], devin["context_lens"], max_ctx, all_reduce)
 
     def step_e2e():
+        if tick:
+            tick()
         d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
         out = hp.step(d["hidden"], d["positions"], d["slot_mapping"], d["block_tables"],
                       d["context_lens"], max_ctx, all_reduce)
@@ -378,6 +465,14 @@ def main():
     ms = e0.elapsed_time(e1)
     attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
     hp.attn_events = None
+
+    # host cost of issuing one step (no device wait): must stay below the device time
+    barrier()
+    h0 = time.perf_counter()
+    for _ in range(3):
+        step_resident()
+    host_ms = (time.perf_counter() - h0) / 3 * 1e3
+    barrier()
 
     # timed region 2: host buffers in, result out, every step
     for _ in range(2):
@@ -433,6 +528,7 @@ def main():
         "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches), "roofline": roofline,
+        "host_issue_ms_per_step": host_ms,
     }
     if rank == 0 and not args.no_cpu_baseline:
         tps, cms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, 2, 1,

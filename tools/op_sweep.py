@@ -108,6 +108,7 @@ def main():
     ap.add_argument("--ops", default="attn,rms,silu,rope,cache")
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default=None, help="attn: cfg:B:mode:version, e.g. 8b-gqa-bf16:256:trace:v1")
     args = ap.parse_args()
     from vllm_ltr_b200 import _C
     ref = load_ref()
@@ -137,12 +138,18 @@ def main():
                  ("8192", [1, 8, 64])]
         if args.quick:
             modes = [("trace", [256]), ("2048", [64])]
+        if args.only:
+            oc, ob, om, ov = args.only.split(":")
+            cfgs = [c for c in cfgs if c[0] == oc]
+            modes = [(om, [int(ob)])]
         for name, hq, hkv, dt, kv in cfgs:
             for mode, Bs in modes:
                 for B in Bs:
                     c = attn_case(B, hq, hkv, dt, kv, mode)
                     for ver in ("v1", "v2"):
                         if ver == "v2" and c["mx"] <= 512:
+                            continue
+                        if args.only and ver != ov:
                             continue
                         ours = timeit(run_attn(_C.ops, c, ver))
                         r = timeit(run_attn(ref.ops, c, ver)) if ref else None

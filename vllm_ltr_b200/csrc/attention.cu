@@ -155,20 +155,22 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     p.max_logits = max_logits;
     p.tmp_out = tmp_out;
   } else {
-    // partition size: enough (sequence, kv head, pass, partition) items for ~3 per resident
-    // warp, at most 512 tokens (one lane-held window of block ids per item, and a short tail),
-    // at least 64 tokens, and no more than 64 partitions per sequence
+    // partition size: enough (sequence, kv head, pass, partition) items to give every resident
+    // warp one, at most 512 tokens (one lane-held window of block ids per item, and a short
+    // tail), at least 64 tokens, and no more than 16 partitions per sequence (the merge of a
+    // sequence is done by one warp)
     const long long slots = (long long)num_sms() * 8;
     const long long groups = (long long)num_seqs * num_kv_heads * p.passes;
-    long long parts_wanted = (3 * slots + groups - 1) / groups;
+    long long parts_wanted = (slots + groups - 1) / groups;
     if (parts_wanted < 1) parts_wanted = 1;
     long long pt = (max_context_len + parts_wanted - 1) / parts_wanted;
-    const long long pt_min = (max_context_len + 63) / 64;
+    const long long pt_min = (max_context_len + 15) / 16;
     if (pt < pt_min) pt = pt_min;
     if (pt < 64) pt = 64;
     int cap = 32 * block_size;
     if (cap > 512) cap = 512;
-    if (pt > cap) pt = cap;
+    if (pt > cap && pt_min <= cap) pt = cap;
+    if (pt > 64 * block_size) pt = 64 * block_size;
     int pb = (int)((pt + block_size - 1) / block_size);
     if (pb < 1) pb = 1;
     if (pb > 64) pb = 64;

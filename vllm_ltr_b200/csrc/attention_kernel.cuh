@@ -313,6 +313,110 @@ __device__ __forceinline__ float load_cg_f(const T* ptr) {
   }
 }
 
+// ---- merge of a sequence's partitions (reference: paged_attention_v2_reduce_kernel, :511-602) ---
+// out[h] = sum_j w_j * tmp[h][j],  w_j = exp_sum_j * exp(max_j - max) / (sum + 1e-6).
+// One warp; lanes own 4 consecutive output elements per 128; HB heads x JB partitions of
+// independent 8/16-byte L2 loads are kept in flight.
+template <typename T>
+__device__ __forceinline__ float4 load_cg_4(const void* base, int64_t elem, bool f32) {
+  if (f32) return __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem));
+  if constexpr (sizeof(T) == 2) {
+    const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(base) + elem));
+    float2 a, b;
+    if constexpr (std::is_same<T, __half>::value) {
+      a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    } else {
+      a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    }
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem));
+  }
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void merge_partials(const Params& p, int seq, int head0, int nheads,
+                                               int np, int lane) {
+  constexpr int HB = 4, JB = 4;
+  constexpr int NV = (D + 127) / 128;   // 4-element vectors per lane
+  for (int h0 = 0; h0 < nheads; h0 += HB) {
+    float mx[HB], inv[HB];
+#pragma unroll
+    for (int hh = 0; hh < HB; ++hh) {
+      const int h = min(h0 + hh, nheads - 1);
+      const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
+      float m = -INFINITY;
+      for (int j = lane; j < np; j += 32) m = fmaxf(m, __ldcg(p.max_logits + base + j));
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int j = lane; j < np; j += 32)
+        sum += __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - m);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mx[hh] = m;
+      inv[hh] = __fdividef(1.0f, sum + 1e-6f);
+    }
+    float4 a[HB][NV];
+#pragma unroll
+    for (int hh = 0; hh < HB; ++hh)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) a[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < np; j0 += JB) {
+      float w[HB][JB];
+      float4 v[HB][JB][NV];
+#pragma unroll
+      for (int hh = 0; hh < HB; ++hh) {
+        const int h = min(h0 + hh, nheads - 1);
+        const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          const int j = min(j0 + jj, np - 1);
+          w[hh][jj] = j0 + jj < np ? __ldcg(p.exp_sums + base + j) *
+                                         expf(__ldcg(p.max_logits + base + j) - mx[hh]) * inv[hh]
+                                   : 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int d = 4 * lane + 128 * i;
+            v[hh][jj][i] = (D % 128 == 0 || d < D)
+                               ? load_cg_4<T>(p.tmp_out, (base + j) * D + d, p.tmp_is_f32 != 0)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < HB; ++hh)
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            a[hh][i].x += v[hh][jj][i].x * w[hh][jj];
+            a[hh][i].y += v[hh][jj][i].y * w[hh][jj];
+            a[hh][i].z += v[hh][jj][i].z * w[hh][jj];
+            a[hh][i].w += v[hh][jj][i].w * w[hh][jj];
+          }
+    }
+#pragma unroll
+    for (int hh = 0; hh < HB; ++hh) {
+      if (h0 + hh < nheads) {
+        T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head0 + h0 + hh) * D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int d = 4 * lane + 128 * i;
+          if (D % 128 == 0 || d < D) {
+            o[d] = ST<T>::from_f(a[hh][i].x);
+            o[d + 1] = ST<T>::from_f(a[hh][i].y);
+            o[d + 2] = ST<T>::from_f(a[hh][i].z);
+            o[d + 3] = ST<T>::from_f(a[hh][i].w);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- work items -----------------------------------------------------------------------------------
 // One item = one partition of one sequence for one kv head and one pass over its query heads.
 struct Item {
@@ -325,11 +429,16 @@ struct Item {
 };
 
 // cum[s] = number of partitions of sequences < s (plan mode), in shared memory
-__device__ __forceinline__ void claim(Item& it, const Params& p, const int* cum, int total_items,
-                                      int part_tokens, int BS, int lane) {
-  int item = 0;
-  if (lane == 0) item = atomicAdd(&p.counters[0], 1);
-  item = __shfl_sync(0xffffffffu, item, 0);
+// The queue ticket is fetched one item AHEAD (lane 0 keeps the pending id in a register and only
+// broadcasts it here), so the atomic's round trip to L2 overlaps the previous item's work.
+__device__ __forceinline__ int fetch_id(const Params& p, int lane) {
+  int id = 0;
+  if (lane == 0) id = atomicAdd(&p.counters[0], 1);
+  return id;
+}
+__device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p, const int* cum,
+                                      int total_items, int part_tokens, int BS, int lane) {
+  const int item = __shfl_sync(0xffffffffu, pending_id, 0);
   it.valid = item < total_items;
   it.issued = 0;
   it.ntiles = 0;
@@ -351,15 +460,20 @@ __device__ __forceinline__ void claim(Item& it, const Params& p, const int* cum,
     it.part = t % p.n_part;
     it.seq = t / p.n_part;
   }
+  it.blk0 = it.part * p.part_blocks;
+  // block ids and the context length are independent loads (one L2 round trip, not two): the
+  // table row is read up to its allocated width and masked by the context afterwards
+  const int32_t* bt = p.block_tables + (int64_t)it.seq * p.max_blocks_per_seq + it.blk0;
+  const int room = min(p.part_blocks, p.max_blocks_per_seq - it.blk0);
+  const int b0 = lane < room ? bt[lane] : 0;
+  const int b1 = 32 + lane < room ? bt[32 + lane] : 0;
   it.ctx = p.context_lens[it.seq];
   const int nblk_ctx = (it.ctx + BS - 1) / BS;
   it.nparts = (it.ctx + part_tokens - 1) / part_tokens;
-  it.blk0 = it.part * p.part_blocks;
   const int blk1 = min(it.blk0 + p.part_blocks, nblk_ctx);
   it.ntiles = max(blk1 - it.blk0, 0);
-  const int32_t* bt = p.block_tables + (int64_t)it.seq * p.max_blocks_per_seq + it.blk0;
-  it.bt0 = lane < it.ntiles ? bt[lane] : 0;
-  it.bt1 = 32 + lane < it.ntiles ? bt[32 + lane] : 0;
+  it.bt0 = lane < it.ntiles ? b0 : 0;
+  it.bt1 = 32 + lane < it.ntiles ? b1 : 0;
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -456,11 +570,27 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     }
   };
 
+  // Work-item lookahead.  The queue ticket for the NEXT item is drawn (async atomic) when the
+  // current item has <= S+2 tiles left, and turned into an item (context length + block ids) once
+  // all tiles of the current item are in flight - late enough not to hoard work other warps could
+  // take, early enough that its tiles are landing while the current item finishes.
   Item cur, nxt;
-  claim(cur, p, cum, total_items, part_tokens, BS, lane);
+  nxt.valid = 0;
+  int pend = fetch_id(p, lane);
+  bool pend_valid = false, nxt_ready = false;
+  claim(cur, pend, p, cum, total_items, part_tokens, BS, lane);
   pump(cur);
-  claim(nxt, p, cum, total_items, part_tokens, BS, lane);
-  pump(nxt);
+  auto advance = [&]() {
+    if (!nxt_ready) {
+      if (!pend_valid) pend = fetch_id(p, lane);
+      claim(nxt, pend, p, cum, total_items, part_tokens, BS, lane);
+    }
+    cur = nxt;
+    nxt.valid = 0;
+    nxt_ready = false;
+    pend_valid = false;
+    pump(cur);
+  };
 
   while (cur.valid) {
     const int seq = cur.seq, part = cur.part, kvh = cur.kvh, ctx = cur.ctx;
@@ -476,10 +606,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head0) * D;
         for (int i = lane; i < nheads * D; i += 32) o[i] = ST<T>::from_f(0.f);
       }
-      cur = nxt;
-      claim(nxt, p, cum, total_items, part_tokens, BS, lane);
-      pump(cur);
-      pump(nxt);
+      advance();
       continue;
     }
 
@@ -547,6 +674,15 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     }
 
     for (int tile = 0; tile < ntiles; ++tile) {
+      if (!pend_valid && !nxt_ready && ntiles - tile <= S + 2) {
+        pend = fetch_id(p, lane);
+        pend_valid = true;
+      } else if (pend_valid && !nxt_ready && cur.issued >= ntiles) {
+        claim(nxt, pend, p, cum, total_items, part_tokens, BS, lane);
+        nxt_ready = true;
+        pend_valid = false;
+        pump(nxt);
+      }
       const uint32_t ktile = tiles_s + stage_c * 2 * C::TILE_BYTES;
       const uint32_t vtile = ktile + C::TILE_BYTES;
       mbar_wait(bars + 8 * stage_c, phase_c);
@@ -759,7 +895,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       }
       // refill the freed stage: this item first, then the next one (lookahead across items)
       pump(cur);
-      pump(nxt);
+      if (nxt_ready) pump(nxt);
     }
 
     // ---- epilogue: finish the reductions, normalise, store / publish the partial ----------------
@@ -846,53 +982,13 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       done = __shfl_sync(0xffffffffu, done, 0);
       if (done == cur.nparts - 1) {
         __threadfence();
-        const int np = cur.nparts;
-        for (int h = 0; h < nheads; ++h) {
-          const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
-          float mx = -INFINITY;
-          for (int j = lane; j < np; j += 32) mx = fmaxf(mx, __ldcg(p.max_logits + base + j));
-#pragma unroll
-          for (int o2 = 16; o2 >= 1; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-          float sum = 0.f;
-          for (int j = lane; j < np; j += 32)
-            sum += __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - mx);
-#pragma unroll
-          for (int o2 = 16; o2 >= 1; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
-          const float inv = __fdividef(1.0f, sum + 1e-6f);
-          float a[(D + 31) / 32];
-#pragma unroll
-          for (int i = 0; i < (D + 31) / 32; ++i) a[i] = 0.f;
-          for (int j = 0; j < np; ++j) {
-            const float w = __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - mx) * inv;
-#pragma unroll
-            for (int i = 0; i < (D + 31) / 32; ++i) {
-              const int d = lane + 32 * i;
-              if (D % 32 == 0 || d < D) {
-                float v;
-                if (p.tmp_is_f32)
-                  v = __ldcg(reinterpret_cast<const float*>(p.tmp_out) + (base + j) * D + d);
-                else
-                  v = load_cg_f<T>(reinterpret_cast<const T*>(p.tmp_out) + (base + j) * D + d);
-                a[i] += v * w;
-              }
-            }
-          }
-          T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head0 + h) * D;
-#pragma unroll
-          for (int i = 0; i < (D + 31) / 32; ++i) {
-            const int d = lane + 32 * i;
-            if (D % 32 == 0 || d < D) o[d] = ST<T>::from_f(a[i]);
-          }
-        }
+        merge_partials<T, D>(p, seq, head0, nheads, cur.nparts, lane);
         if (lane == 0) p.tickets[gid] = 0;   // leave the ticket table clean for the next launch
       }
     }
     __syncwarp();  // q_s / p_s are rewritten by the next item
 
-    cur = nxt;
-    claim(nxt, p, cum, total_items, part_tokens, BS, lane);
-    pump(cur);
-    pump(nxt);
+    advance();
   }
 
   // self-resetting queue: the last warp to leave zeroes the counters for the next launch

@@ -75,6 +75,44 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     return out
 
 
+def dummy_checkpoint(kind: str = "125m", seed: int = 0, num_labels: int = 1,
+                     vocab: int = 50272, max_pos: int = 2048):
+    """(config, state_dict) with seeded random weights in the OPT-125M / OPT-350M predictor layouts
+    - the counterpart of the reference's ``--load-format dummy`` (model_loader/loader.py:246) for
+    benchmarks without checkpoints."""
+    if kind == "125m":
+        cfg = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, ffn_dim=3072,
+                   word_embed_proj_dim=768, do_layer_norm_before=True)
+    elif kind == "350m":
+        cfg = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, ffn_dim=4096,
+                   word_embed_proj_dim=512, do_layer_norm_before=False)
+    else:
+        raise ValueError(kind)
+    cfg.update(vocab_size=vocab, max_position_embeddings=max_pos, num_labels=num_labels,
+               activation_function="relu", _remove_final_layer_norm=False)
+    g = torch.Generator().manual_seed(seed)
+    H, E, Fd = cfg["hidden_size"], cfg["word_embed_proj_dim"], cfg["ffn_dim"]
+    w = lambda *shape, std=0.02: (torch.randn(*shape, generator=g) * std).to(torch.float16)
+    sd = {"model.decoder.embed_tokens.weight": w(vocab, E),
+          "model.decoder.embed_positions.weight": w(max_pos + 2, H),
+          "score.weight": w(num_labels, E, std=0.05)}
+    if E != H:
+        sd["model.decoder.project_in.weight"] = w(H, E)
+        sd["model.decoder.project_out.weight"] = w(E, H)
+    if cfg["do_layer_norm_before"]:
+        sd["model.decoder.final_layer_norm.weight"] = 1 + w(H, std=0.1)
+        sd["model.decoder.final_layer_norm.bias"] = w(H)
+    for i in range(cfg["num_hidden_layers"]):
+        p = f"model.decoder.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[p + f"self_attn.{n}.weight"], sd[p + f"self_attn.{n}.bias"] = w(H, H, std=0.04), w(H)
+        sd[p + "fc1.weight"], sd[p + "fc1.bias"] = w(Fd, H, std=0.04), w(Fd)
+        sd[p + "fc2.weight"], sd[p + "fc2.bias"] = w(H, Fd, std=0.04), w(H)
+        for n in ("self_attn_layer_norm", "final_layer_norm"):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = 1 + w(H, std=0.1), w(H)
+    return cfg, sd
+
+
 class OPTPredictor:
     """OPTForSequenceClassification forward (vllm/model_executor/models/opt.py:362-397) on the
     GPU.  ``state_dict`` uses the HF checkpoint names the reference's load_weights consumes

@@ -119,7 +119,7 @@ class GpuTick:
         cfg, sd = dummy_checkpoint("125m", seed=0)
         self.pred = OPTPredictor(cfg, sd, device=dev)
         self.ranker = GpuRanker()
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)   # ahead of the model stream
         self.last = None
 
     def __call__(self):
@@ -305,8 +305,8 @@ def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_bat
 
     for _ in range(warmup):
         one()
-        if tick:
-            tick()
+    for _ in range(2 if tick else 0):      # first calls pay thread-pool / allocator start-up
+        tick()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
@@ -423,19 +423,23 @@ def main():
     # the scheduler (and with it the tick) lives on the driver rank only
     tick = GpuTick(dev, args.live_requests, args.tick_prompt_len) if (args.tick and rank == 0) else None
 
+    # Order inside a step: the model stream gets its work first, then the scheduler's tick for the
+    # NEXT step (score the prompt that arrived meanwhile, re-rank the queue) runs on its own
+    # stream while the model executes, and the host waits for both.
     def step_resident():
+        out = hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                      devin["block_tables"], devin["context_lens"], max_ctx, all_reduce)
         if tick:
             tick()
-        return hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
-                       devin["block_tables"], devin["context_lens"], max_ctx, all_reduce)
+        return out
 
     def step_e2e():
-        if tick:
-            tick()
         d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
         out = hp.step(d["hidden"], d["positions"], d["slot_mapping"], d["block_tables"],
                       d["context_lens"], max_ctx, all_reduce)
         out_host.copy_(out, non_blocking=True)
+        if tick:
+            tick()
         torch.cuda.current_stream().synchronize()      # the engine samples from this result
 
     def barrier():
@@ -466,13 +470,21 @@ def main():
     attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
     hp.attn_events = None
 
-    # host cost of issuing one step (no device wait): must stay below the device time
+    # host cost of issuing the decode ops of one step (no device wait, tick excluded): must
+    # stay below the device time or the step becomes launch-bound
     barrier()
     h0 = time.perf_counter()
     for _ in range(3):
-        step_resident()
+        hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                devin["block_tables"], devin["context_lens"], max_ctx, all_reduce)
     host_ms = (time.perf_counter() - h0) / 3 * 1e3
     barrier()
+    tick_ms = None
+    if tick:
+        h0 = time.perf_counter()
+        for _ in range(3):
+            tick()
+        tick_ms = (time.perf_counter() - h0) / 3 * 1e3      # GPU otherwise idle: tick latency
 
     # timed region 2: host buffers in, result out, every step
     for _ in range(2):
@@ -528,7 +540,7 @@ def main():
         "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches), "roofline": roofline,
-        "host_issue_ms_per_step": host_ms,
+        "host_issue_ms_per_step": host_ms, "tick_ms_alone": tick_ms,
     }
     if rank == 0 and not args.no_cpu_baseline:
         tps, cms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, 2, 1,

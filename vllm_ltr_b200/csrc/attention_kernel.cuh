@@ -507,26 +507,29 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   int total_items;
   if (p.use_plan) {
     // partition plan: exclusive prefix sums of the per-sequence partition counts (every CTA
-    // builds its own copy: num_seqs <= 2048 integers)
+    // builds its own copy: num_seqs <= 2048 integers).  All threads fetch the context lengths
+    // at once (one L2 round trip), warp 0 scans them out of shared memory.
+    for (int s = threadIdx.x; s < p.num_seqs; s += blockDim.x) {
+      const int c = p.context_lens[s];
+      cum[s + 1] = c > 0 ? (c + part_tokens - 1) / part_tokens : 1;   // empty context: one item writes zeros
+    }
+    __syncthreads();
     if (warp == 0) {
       int carry = 0;
       for (int base = 0; base < p.num_seqs; base += 32) {
         const int s = base + lane;
-        int n = 0;
-        if (s < p.num_seqs) {
-          const int c = p.context_lens[s];
-          n = c > 0 ? (c + part_tokens - 1) / part_tokens : 1;   // empty context: one item writes zeros
-        }
+        const int n = s < p.num_seqs ? cum[s + 1] : 0;
         int incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int v = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += v;
         }
-        if (s < p.num_seqs) cum[s] = carry + incl - n;
+        __syncwarp();
+        if (s < p.num_seqs) cum[s + 1] = carry + incl;
         carry += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) cum[p.num_seqs] = carry;
+      if (lane == 0) cum[0] = 0;
     }
     __syncthreads();
     total_items = cum[p.num_seqs] * p.passes * p.num_kv_heads;

@@ -194,6 +194,8 @@ class OPTPredictor:
         self.max_batch_prompts = max_batch_prompts
         self._ws = None
         self._ws_cap = (0, 0)
+        self._host = None
+        self._host_evt = None
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -248,8 +250,14 @@ class OPTPredictor:
         if max(lens) > self.max_pos:
             raise RuntimeError(f"prompt of {max(lens)} tokens exceeds max_position_embeddings")
         n, m = len(batch), sum(lens)
-        # one pinned staging buffer, one H2D copy: ids | positions | cu_seqlens | last_rows
-        host = torch.empty(2 * m + 2 * n + 1, dtype=torch.int32).pin_memory()
+        # one pinned staging buffer (persistent, grow-only), one H2D copy:
+        # ids | positions | cu_seqlens | last_rows
+        need = 2 * m + 2 * n + 1
+        if self._host is None or self._host.numel() < need:
+            self._host = torch.empty(max(need, 8192), dtype=torch.int32).pin_memory()
+        if self._host_evt is not None:
+            self._host_evt.synchronize()          # the previous copy out of the buffer is done
+        host = self._host[:need]
         ids, pos = host[:m], host[m:2 * m]
         cu, last = host[2 * m:2 * m + n + 1], host[2 * m + n + 1:]
         o = 0
@@ -261,6 +269,8 @@ class OPTPredictor:
             cu[k + 1] = o
             last[k] = o - 1
         d = host.to(self.device, non_blocking=True)
+        self._host_evt = torch.cuda.Event()
+        self._host_evt.record()
         ws, ws_bytes = self._workspace(m, n)
         base = d.data_ptr()
         with torch.cuda.device(self.device):

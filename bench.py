@@ -285,6 +285,13 @@ def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_bat
         sample_layers = 1
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    # torchrun exports OMP_NUM_THREADS=1; the reference kernels read the OpenMP runtime directly
+    import ctypes
+    for so in ("libgomp.so.1",):
+        try:
+            ctypes.CDLL(so).omp_set_num_threads(cores)
+        except OSError:
+            pass
     cshape = ModelShape(**{**shape.__dict__})
     if cshape.dtype == torch.float16:
         cshape.dtype = torch.bfloat16        # csrc/cpu implements f32 and bf16 only

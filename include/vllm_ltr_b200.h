@@ -190,6 +190,31 @@ int vltr_opt_forward(const void* handle, const int32_t* token_ids, const int32_t
 int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias, const void* resid, int M,
                   int N, int K, int relu, int dtype, void* stream);
 
+/* ---- tensor-parallel exchange (config 5: 70B at TP=8) ------------------------------------------
+ * Replaces tensor_model_parallel_all_reduce (vllm/distributed/communication_op.py:13-42; reference
+ * kernels csrc/custom_all_reduce.cuh:181-250, entry csrc/custom_all_reduce.cu:101-122) and, fused
+ * with it, the fused_add_rms_norm that consumes every all-reduced row-parallel GEMM output
+ * (vllm/model_executor/models/llama.py:236-238, csrc/layernorm_kernels.cu:318-352).
+ * x / out / resid are SYMMETRIC buffers: one per rank, same shape [num_tokens, hidden], every
+ * rank holds all ranks' device pointers (x_ptrs[p] etc. are HOST arrays of `world` peer-mapped
+ * device pointers, e.g. from torch.distributed._symmetric_memory); signal_pads[p] is rank p's
+ * zero-initialised flag area (>= 8 KiB).  Every rank calls with the same sizes; one kernel per
+ * rank, CTAs rendezvous across ranks through the signal pads.
+ *   vltr_tp_allreduce:               out[p] = sum_q x[q]                      on every rank p
+ *   vltr_tp_allreduce_add_rms_norm:  resid[p] = (T)(sum_q x[q]) + resid ; out[p] = rms_norm(resid[p]) * weight
+ * fp32 accumulation in rank order, results identical on all ranks. */
+typedef struct vltr_tp_comm {
+  int rank, world;
+  const void* const* x_ptrs;
+  void* const* out_ptrs;
+  void* const* resid_ptrs;        /* may be NULL for vltr_tp_allreduce */
+  uint32_t* const* signal_pads;
+} vltr_tp_comm;
+int vltr_tp_allreduce(const vltr_tp_comm* comm, int num_tokens, int hidden_size, int dtype,
+                      void* stream);
+int vltr_tp_allreduce_add_rms_norm(const vltr_tp_comm* comm, const void* weight, float epsilon,
+                                   int num_tokens, int hidden_size, int dtype, void* stream);
+
 /* ---- cuda utils: csrc/cuda_utils_kernels.cu ---------------------------------------------- */
 int vltr_get_device_attribute(int attribute, int device_id);
 int vltr_get_max_shared_memory_per_block_device_attribute(int device_id);

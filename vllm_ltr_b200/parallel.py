@@ -53,3 +53,80 @@ def all_reduce_into(inp: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     if out.data_ptr() != inp.data_ptr():
         out.copy_(inp)
     return tensor_model_parallel_all_reduce(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused exchange + norm over NVLink peer memory (csrc/tp_allreduce.cu)
+# ---------------------------------------------------------------------------------------------
+class FusedTPComm:
+    """Symmetric activation buffers of one tensor-parallel rank and the fused
+    ``all_reduce + residual add + RMSNorm`` that replaces ``tensor_model_parallel_all_reduce``
+    (communication_op.py:13-42) followed by ``fused_add_rms_norm`` (llama.py:236-238).
+
+    ``x[i]`` are the buffers the row-parallel GEMMs (o_proj, down_proj) write their partial sums
+    into, ``out`` receives the normalised rows and ``resid`` is the running residual - all
+    allocated from ``torch.distributed._symmetric_memory`` so every rank holds every rank's
+    pointers (plumbing only; the data path is the kernel in libvllm_ltr_b200)."""
+
+    def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device,
+                 group: Optional[dist.ProcessGroup] = None, num_inputs: int = 2):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import declare
+        self._ct = ctypes
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world < 2 or self.world > 8:
+            raise RuntimeError(f"FusedTPComm supports 2..8 ranks, got {self.world}")
+        self.hidden, self.dtype, self.max_tokens = hidden, dtype, max_tokens
+        name = group.group_name
+        try:
+            symm.enable_symm_mem_for_group(name)
+        except Exception:      # newer torch enables groups on rendezvous
+            pass
+        mk = lambda: symm.empty(max_tokens, hidden, dtype=dtype, device=device)
+        self.x = [mk() for _ in range(num_inputs)]
+        self.out, self.resid = mk(), mk()
+        hx = [symm.rendezvous(t, name) for t in self.x]
+        ho, hr = symm.rendezvous(self.out, name), symm.rendezvous(self.resid, name)
+        self._handles = hx + [ho, hr]
+        arr = lambda ptrs: (ctypes.c_void_p * self.world)(*[int(p) for p in ptrs])
+        self._x_ptrs = [arr(h.buffer_ptrs) for h in hx]
+        self._out_ptrs, self._resid_ptrs = arr(ho.buffer_ptrs), arr(hr.buffer_ptrs)
+        self._pads = arr(hx[0].signal_pad_ptrs)
+
+        class _Comm(ctypes.Structure):
+            _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int),
+                        ("x_ptrs", ctypes.c_void_p), ("out_ptrs", ctypes.c_void_p),
+                        ("resid_ptrs", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p)]
+
+        addr = lambda a: ctypes.cast(a, ctypes.c_void_p)
+        self._comms = [_Comm(self.rank, self.world, addr(xp), addr(self._out_ptrs),
+                             addr(self._resid_ptrs), addr(self._pads)) for xp in self._x_ptrs]
+        _P = ctypes.c_void_p
+        self._norm = declare("vltr_tp_allreduce_add_rms_norm", ctypes.c_int,
+                             [_P, _P, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P])
+        self._plain = declare("vltr_tp_allreduce", ctypes.c_int,
+                              [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P])
+        self._code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dtype]
+        dist.barrier(group)
+
+    def _stream(self):
+        return torch._C._cuda_getCurrentRawStream(self.out.device.index)
+
+    def allreduce_add_rms_norm(self, which: int, weight: torch.Tensor, eps: float,
+                               num_tokens: int) -> torch.Tensor:
+        """resid = (T)(sum over ranks of x[which]) + resid; returns out = rms_norm(resid) * weight
+        (rows [:num_tokens]); identical on every rank."""
+        from ._lib import check
+        check(self._norm(self._ct.byref(self._comms[which]), weight.data_ptr(), eps, num_tokens,
+                         self.hidden, self._code, self._stream()))
+        return self.out[:num_tokens]
+
+    def allreduce(self, which: int, num_tokens: int) -> torch.Tensor:
+        """out = sum over ranks of x[which] (rows [:num_tokens])."""
+        from ._lib import check
+        check(self._plain(self._ct.byref(self._comms[which]), num_tokens, self.hidden, self._code,
+                          self._stream()))
+        return self.out[:num_tokens]

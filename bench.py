@@ -349,6 +349,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--cpu-sample-batch", type=int, default=256)
+    ap.add_argument("--tp-exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused peer-memory all-reduce+norm kernel, or NCCL all_reduce + norm")
     ap.add_argument("--no-tick", dest="tick", action="store_false",
                     help="leave the LTR scheduling tick (a8, a10) out of the step")
     ap.add_argument("--live-requests", type=int, default=10000,
@@ -379,6 +381,7 @@ def main():
                    if args.tick else ""))
     config = {"workload": workload, "batch": args.batch, "layers": bench_shape.layers,
               "sum_context_tokens": int(ctx.sum()), "parallelism": f"tp{world}",
+              "tp_exchange": (args.tp_exchange if world > 1 else None),
               "l2": "inputs larger than L2 (each layer reads its own KV pool)"}
 
     # ---------------- reference arm: CPU kernels on host cores, rank 0 only ----------------
@@ -424,8 +427,12 @@ def main():
 
     all_reduce = None
     if world > 1:
-        from vllm_ltr_b200.parallel import tensor_model_parallel_all_reduce
-        all_reduce = tensor_model_parallel_all_reduce
+        if args.tp_exchange == "fused":
+            from vllm_ltr_b200.parallel import FusedTPComm
+            hp.attach_fused_tp(FusedTPComm(args.batch, shape.hidden, shape.dtype, dev))
+        else:
+            from vllm_ltr_b200.parallel import tensor_model_parallel_all_reduce
+            all_reduce = tensor_model_parallel_all_reduce
 
     # the scheduler (and with it the tick) lives on the driver rank only
     tick = GpuTick(dev, args.live_requests, args.tick_prompt_len) if (args.tick and rank == 0) else None

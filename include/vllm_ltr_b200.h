@@ -198,13 +198,15 @@ int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias, const
  * x / out / resid are SYMMETRIC buffers: one per rank, same shape [num_tokens, hidden], every
  * rank holds all ranks' device pointers (x_ptrs[p] etc. are HOST arrays of `world` peer-mapped
  * device pointers, e.g. from torch.distributed._symmetric_memory); signal_pads[p] is rank p's
- * zero-initialised flag area (>= 8 KiB).  Every rank calls with the same sizes; one kernel per
- * rank, CTAs rendezvous across ranks through the signal pads.
+ * zero-initialised flag area (>= 8 KiB).  Every rank calls with the same sizes and epoch; one
+ * kernel per rank, ranks rendezvous through epoch flags in the signal pads.
  *   vltr_tp_allreduce:               out[p] = sum_q x[q]                      on every rank p
  *   vltr_tp_allreduce_add_rms_norm:  resid[p] = (T)(sum_q x[q]) + resid ; out[p] = rms_norm(resid[p]) * weight
  * fp32 accumulation in rank order, results identical on all ranks. */
 typedef struct vltr_tp_comm {
   int rank, world;
+  uint32_t epoch;                 /* 2 * k + 1 for the k-th exchange on these buffers (k = 0, 1, ...):
+                                     every rank passes the same value, strictly increasing */
   const void* const* x_ptrs;
   void* const* out_ptrs;
   void* const* resid_ptrs;        /* may be NULL for vltr_tp_allreduce */

@@ -18,9 +18,10 @@
 //   * so each row is reduced and normalised exactly once in the whole group (world x less norm
 //     work than the replicated fused_add_rms_norm), and per GPU ~T*H*s*(world-1)/world bytes come
 //     in and twice that go out - no intermediate buffer, no second launch;
-//   * CTAs of the same index on all ranks rendezvous through flags in the peers' signal pads
-//     (system-scope CAS: 0->1 by the sender, 1->0 by the receiver, self-resetting) before reading
-//     peer rows and after the peer stores; spins are bounded and trap instead of hanging.
+//   * ranks rendezvous before reading peer rows and after the peer stores through monotonically
+//     increasing epoch flags in the peers' signal pads: one-way release stores over NVLink and
+//     local acquire polls (no round trips, nothing to reset); one CTA per rank talks to the
+//     peers, the rest follow a device-scope flag; spins are bounded and trap instead of hanging.
 // The plain all-reduce (no norm) uses the same machinery for callers that need it.
 #include "common.cuh"
 
@@ -28,9 +29,10 @@ namespace vltr {
 namespace tp {
 
 constexpr int kMaxWorld = 8;
-constexpr int kMaxCtas = 64;           // barrier channels available in the signal pad
 constexpr int kPadBase = 1024;         // our flags start here (u32 index); torch's own barrier uses the front
-constexpr int kThreads = 512;
+constexpr int kThreads = 256;
+// signal-pad layout (u32 index from kPadBase): [0..7] arrival epoch of rank p (written by p),
+// [8] local "go" epoch (CTA 0 -> the other CTAs of this rank), [9] local count of finished CTAs
 
 struct Comm {
   const void* x[kMaxWorld];            // every rank's x buffer (index = rank)
@@ -38,31 +40,43 @@ struct Comm {
   void* resid[kMaxWorld];
   uint32_t* pad[kMaxWorld];            // every rank's signal pad
   int rank, world;
+  uint32_t epoch;                      // 2 * call_index + 1 (start barrier), + 2 (end barrier)
 };
 
 __device__ __forceinline__ void spin_trap() {
   printf("vltr tp_allreduce: peer barrier timed out\n");
   __trap();
 }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
-// CTA `cta` of every rank meets here.  `release` makes this CTA's prior global / peer stores
-// visible system-wide first.
-__device__ __forceinline__ void peer_barrier(const Comm& c, int cta, bool release) {
-  if (release) __threadfence_system();
-  __syncthreads();
+// All ranks meet: every rank writes `epoch` into its slot of every peer's pad (one-way NVLink
+// stores, no round trips) and waits until all slots of its own pad have reached `epoch`.
+// Epochs grow monotonically, so flags never need resetting.  Called by ONE CTA per rank.
+__device__ __forceinline__ void peer_barrier(const Comm& c, uint32_t epoch) {
   if (threadIdx.x < c.world) {
     const int peer = threadIdx.x;
-    uint32_t* remote = c.pad[peer] + kPadBase + cta * kMaxWorld + c.rank;
-    uint32_t* local = c.pad[c.rank] + kPadBase + cta * kMaxWorld + peer;
+    st_release_sys(c.pad[peer] + kPadBase + c.rank, epoch);
+    const uint32_t* mine = c.pad[c.rank] + kPadBase + peer;
     long long spins = 0;
-    while (atomicCAS_system(remote, 0u, 1u) != 0u)
-      if (++spins > (1ll << 28)) spin_trap();
-    spins = 0;
-    while (atomicCAS_system(local, 1u, 0u) != 1u)
-      if (++spins > (1ll << 28)) spin_trap();
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0)
+      if (++spins > (1ll << 30)) spin_trap();
   }
   __syncthreads();
-  __threadfence_system();
 }
 
 __device__ __forceinline__ uint4 ld_peer(const void* p) {
@@ -102,8 +116,22 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ float red[32];
   const int cta = blockIdx.x;
   const int nvec = hidden / N;
+  uint32_t* go = c.pad[c.rank] + kPadBase + 8;
+  uint32_t* fin = c.pad[c.rank] + kPadBase + 9;
 
-  peer_barrier(c, cta, false);      // every rank's x is complete (their previous kernels finished)
+  // start: every rank's x is complete (its producing kernels finished before this one started).
+  // CTA 0 meets the peers and releases the other CTAs of this rank.
+  if (cta == 0) {
+    peer_barrier(c, c.epoch);
+    if (threadIdx.x == 0) st_release_gpu(go, c.epoch);
+  } else {
+    if (threadIdx.x == 0) {
+      long long spins = 0;
+      while ((int32_t)(ld_acquire_gpu(go) - c.epoch) < 0)
+        if (++spins > (1ll << 30)) spin_trap();
+    }
+    __syncthreads();
+  }
 
   // rows owned by this rank: r, r + world, ...; CTAs of this rank stride over them
   for (int row = c.rank + cta * c.world; row < num_tokens; row += gridDim.x * c.world) {
@@ -188,7 +216,18 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
   }
-  peer_barrier(c, cta, true);       // all rows of all ranks have landed everywhere
+  // end: all rows of all ranks have landed everywhere.  The last CTA of this rank to finish
+  // its peer stores meets the peers.
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(fin, 1u);
+    s_last = done == gridDim.x - 1;
+    if (s_last) *fin = 0u;
+  }
+  __syncthreads();
+  if (s_last) peer_barrier(c, c.epoch + 1);
 }
 
 template <typename T, bool NORM>
@@ -197,9 +236,9 @@ static int launch(const Comm& c, const void* weight, float eps, int num_tokens, 
   constexpr int N = 16 / sizeof(T);
   const int nvec = hidden / N;
   const int rows_mine = (num_tokens - c.rank + c.world - 1) / c.world;
-  // every rank must launch the same grid (CTA b meets CTA b of the peers)
+  // one CTA per owned row, up to two per SM (they loop beyond that)
   int grid = (num_tokens + c.world - 1) / c.world;
-  if (grid > kMaxCtas) grid = kMaxCtas;
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
   if (grid < 1) grid = 1;
   (void)rows_mine;
   const int vpt = (nvec + kThreads - 1) / kThreads;
@@ -209,6 +248,8 @@ static int launch(const Comm& c, const void* weight, float eps, int num_tokens, 
     tp_fused_kernel<T, 2, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
   else if (vpt <= 4)
     tp_fused_kernel<T, 4, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
+  else if (vpt <= 8)
+    tp_fused_kernel<T, 8, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
   else
     return fail(VLTR_ERR_UNSUPPORTED, "tp_allreduce: hidden size %d too large", hidden);
   VLTR_LAUNCH_CHECK(NORM ? "tp_allreduce_add_rms_norm" : "tp_allreduce");
@@ -229,9 +270,12 @@ static int run(const vltr_tp_comm* comm, const void* weight, float eps, int num_
   VLTR_CHECK(hidden % n == 0, VLTR_ERR_UNSUPPORTED,
              "tp_allreduce: hidden %d must be a multiple of %d", hidden, n);
   if (num_tokens == 0) return VLTR_OK;
+  VLTR_CHECK(comm->epoch % 2 == 1, VLTR_ERR_INVALID,
+             "tp_allreduce: epoch must be odd (2 * call_index + 1), got %u", comm->epoch);
   Comm c{};
   c.rank = comm->rank;
   c.world = comm->world;
+  c.epoch = comm->epoch;
   for (int p = 0; p < comm->world; ++p) {
     c.x[p] = comm->x_ptrs[p];
     c.out[p] = comm->out_ptrs[p];

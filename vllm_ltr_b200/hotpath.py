@@ -164,11 +164,60 @@ class DecodeHotPath:
         self.scale = float(scale)
         self.attn_events = None   # optional [(start, end)] CUDA events around each attention call
 
+    def attach_fused_tp(self, comm) -> None:
+        """Tensor-parallel mode with the fused exchange (vllm_ltr_b200.parallel.FusedTPComm): the
+        row-parallel GEMM outputs, the residual and the normed activations live in the
+        communicator's symmetric buffers; every ``all_reduce + fused_add_rms_norm`` pair of the
+        layer becomes one ``allreduce_add_rms_norm`` call."""
+        self.comm = comm
+        comm.x[0][:self.o_proj_out.shape[0]].copy_(self.o_proj_out)
+        comm.x[1][:self.down_out.shape[0]].copy_(self.down_out)
+
+    def _step_fused_tp(self, hidden_in, positions, slot_mapping, block_tables, context_lens,
+                       max_context_len) -> torch.Tensor:
+        s, comm = self.shape, self.comm
+        ops, cache_ops = self.C.ops, self.C.cache_ops
+        T = hidden_in.shape[0]
+        qsz, kvsz = s.q_heads * s.head_size, s.kv_heads * s.head_size
+        q, k, v = self.qkv[:T].split([qsz, kvsz, kvsz], dim=-1)
+        attn_out = self.attn_out[:T]
+        for layer in range(self.layers):
+            if layer == 0:
+                # embedding output is replicated on every rank: plain local norm
+                comm.resid[:T].copy_(hidden_in)
+                ops.rms_norm(comm.out[:T], comm.resid[:T], self.norm_w[0], s.eps)
+            else:
+                # previous down_proj exchange + this layer's input_layernorm
+                comm.allreduce_add_rms_norm(1, self.norm_w[2 * layer], s.eps, T)
+            ops.rotary_embedding(positions, q, k, s.head_size, self.cos_sin, True)
+            kc, vc = self.key_caches[layer], self.value_caches[layer]
+            cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
+                                        v.view(T, s.kv_heads, s.head_size), kc, vc, slot_mapping,
+                                        s.kv_cache_dtype, 1.0)
+            ev = self.attn_events
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            forward_decode(q.view(T, s.q_heads, s.head_size), kc, vc, block_tables, context_lens,
+                           max_context_len, s.kv_cache_dtype, s.kv_heads, self.scale, None, 1.0,
+                           out=attn_out.view(T, s.q_heads, s.head_size), C=self.C)
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
+            # o_proj exchange + post_attention_layernorm
+            comm.allreduce_add_rms_norm(0, self.norm_w[2 * layer + 1], s.eps, T)
+            ops.silu_and_mul(self.act_out[:T], self.gate_up[:T])
+        # last down_proj exchange + final norm
+        return comm.allreduce_add_rms_norm(1, self.norm_w[2 * self.layers], s.eps, T)
+
     def step(self, hidden_in: torch.Tensor, positions: torch.Tensor, slot_mapping: torch.Tensor,
              block_tables: torch.Tensor, context_lens: torch.Tensor, max_context_len: int,
              all_reduce=None) -> torch.Tensor:
         """One decode step for ``T = hidden_in.shape[0]`` sequences (one new token each).
         Returns the final-norm output [T, hidden] (what compute_logits consumes)."""
+        if getattr(self, "comm", None) is not None:
+            return self._step_fused_tp(hidden_in, positions, slot_mapping, block_tables,
+                                       context_lens, max_context_len)
         s = self.shape
         ops, cache_ops = self.C.ops, self.C.cache_ops
         T = hidden_in.shape[0]

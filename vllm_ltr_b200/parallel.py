@@ -81,10 +81,6 @@ class FusedTPComm:
             raise RuntimeError(f"FusedTPComm supports 2..8 ranks, got {self.world}")
         self.hidden, self.dtype, self.max_tokens = hidden, dtype, max_tokens
         name = group.group_name
-        try:
-            symm.enable_symm_mem_for_group(name)
-        except Exception:      # newer torch enables groups on rendezvous
-            pass
         mk = lambda: symm.empty(max_tokens, hidden, dtype=dtype, device=device)
         self.x = [mk() for _ in range(num_inputs)]
         self.out, self.resid = mk(), mk()
@@ -98,11 +94,12 @@ class FusedTPComm:
 
         class _Comm(ctypes.Structure):
             _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int),
-                        ("x_ptrs", ctypes.c_void_p), ("out_ptrs", ctypes.c_void_p),
+                        ("epoch", ctypes.c_uint32), ("x_ptrs", ctypes.c_void_p), ("out_ptrs", ctypes.c_void_p),
                         ("resid_ptrs", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p)]
 
         addr = lambda a: ctypes.cast(a, ctypes.c_void_p)
-        self._comms = [_Comm(self.rank, self.world, addr(xp), addr(self._out_ptrs),
+        self._calls = 0       # exchanges issued on these buffers (same on every rank)
+        self._comms = [_Comm(self.rank, self.world, 1, addr(xp), addr(self._out_ptrs),
                              addr(self._resid_ptrs), addr(self._pads)) for xp in self._x_ptrs]
         _P = ctypes.c_void_p
         self._norm = declare("vltr_tp_allreduce_add_rms_norm", ctypes.c_int,
@@ -120,6 +117,8 @@ class FusedTPComm:
         """resid = (T)(sum over ranks of x[which]) + resid; returns out = rms_norm(resid) * weight
         (rows [:num_tokens]); identical on every rank."""
         from ._lib import check
+        self._comms[which].epoch = (2 * self._calls + 1) & 0xFFFFFFFF
+        self._calls += 1
         check(self._norm(self._ct.byref(self._comms[which]), weight.data_ptr(), eps, num_tokens,
                          self.hidden, self._code, self._stream()))
         return self.out[:num_tokens]
@@ -127,6 +126,8 @@ class FusedTPComm:
     def allreduce(self, which: int, num_tokens: int) -> torch.Tensor:
         """out = sum over ranks of x[which] (rows [:num_tokens])."""
         from ._lib import check
+        self._comms[which].epoch = (2 * self._calls + 1) & 0xFFFFFFFF
+        self._calls += 1
         check(self._plain(self._ct.byref(self._comms[which]), num_tokens, self.hidden, self._code,
                           self._stream()))
         return self.out[:num_tokens]

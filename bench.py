@@ -338,6 +338,17 @@ def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_bat
 
 # ---------------------------------------------------------------------------------------------
 def main():
+    # the driver reads ONE JSON line from stdout: libraries that print there (NCCL's version
+    # banner) are pointed at stderr, the line goes to the real stdout at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -391,7 +402,7 @@ def main():
         tps, ms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, args.steps,
                                                        args.warmup, args.cpu_sample_layers,
                                                        args.cpu_sample_batch)
-        print(json.dumps({
+        print(file=out, flush=True, *[json.dumps({
             "impl": "reference", "metric": "output_tokens_per_s", "value": tps,
             "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -400,7 +411,7 @@ def main():
                              "sample": desc},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})])
         return
 
     # ---------------- our arm ----------------
@@ -563,7 +574,7 @@ def main():
         line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind,
                                 "sample": desc, "ms_per_step": cms}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

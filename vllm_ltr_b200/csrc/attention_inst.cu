@@ -17,7 +17,6 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
   auto kern = paged_attention_kernel<T, CT, D, BS, GT, MMA>;
   // per-instantiation launch plan, computed once: stages, warps/CTA, CTAs/SM
   struct Plan { int stages, warps, smem, ctas_per_sm; bool ok; };
-  constexpr int kPlanBytes = (kMaxPlanSeqs + 1) * 4;
   static Plan plan = [&]() {
     Plan pl{0, 0, 0, 0, false};
     int dev = 0, max_optin = 0;

@@ -42,7 +42,8 @@ namespace attn {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kMaxPlanSeqs = 2048;   // per-CTA partition plan (prefix sums) lives in smem up to here
+constexpr int kMaxPlanSeqs = 1024;   // per-CTA partition plan lives in shared memory up to here
+constexpr int kPlanBytes = 8192;     // cum[n+1] ints + 2 x 66 ints (tail histogram) + n uint16
 
 struct Params {
   void* out;                    // [num_seqs, num_heads, D]  T
@@ -436,8 +437,14 @@ __device__ __forceinline__ int fetch_id(const Params& p, int lane) {
   if (lane == 0) id = atomicAdd(&p.counters[0], 1);
   return id;
 }
-__device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p, const int* cum,
+struct Plan {
+  const int* cum;                   // [n+1] exclusive prefix sums of FULL partitions per sequence
+  const unsigned short* tail_order; // sequences that end in a partial partition, longest tail first
+  int n_full;                       // total number of full partitions
+};
+__device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p, const Plan& plan,
                                       int total_items, int part_tokens, int BS, int lane) {
+  const int* cum = plan.cum;
   const int item = __shfl_sync(0xffffffffu, pending_id, 0);
   it.valid = item < total_items;
   it.issued = 0;
@@ -447,18 +454,30 @@ __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p,
   int t = item / p.num_kv_heads;
   it.pass = t % p.passes;
   t /= p.passes;
+  bool tail_item = false;
   if (p.use_plan) {
-    // largest s with cum[s] <= t
-    int lo = 0, hi = p.num_seqs;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (cum[mid] <= t) lo = mid; else hi = mid;
+    // longest-processing-time-first order: all full partitions (part_tokens each), then the
+    // partial tails sorted by length
+    if (t < plan.n_full) {
+      int lo = 0, hi = p.num_seqs;     // largest s with cum[s] <= t
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cum[mid] <= t) lo = mid; else hi = mid;
+      }
+      it.seq = lo;
+      it.part = t - cum[lo];
+    } else {
+      it.seq = plan.tail_order[t - plan.n_full];
+      it.part = 0;
+      tail_item = true;
     }
-    it.seq = lo;
-    it.part = t - cum[lo];
   } else {
     it.part = t % p.n_part;
     it.seq = t / p.n_part;
+  }
+  if (tail_item) {    // the tail is the sequence's last partition: its index needs the context
+    it.ctx = p.context_lens[it.seq];
+    it.part = it.ctx / part_tokens;
   }
   it.blk0 = it.part * p.part_blocks;
   // block ids and the context length are independent loads (one L2 round trip, not two): the
@@ -497,7 +516,10 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   const uint32_t bars = smem_u32(reinterpret_cast<unsigned char*>(p_s) +
                                  ((C::P_BYTES + 15) / 16) * 16);   // S mbarriers
   const uint32_t q_sa = smem_u32(q_s), p_sa = smem_u32(p_s);
-  int* cum = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * wbytes);   // [num_seqs + 1]
+  int* cum = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * wbytes);   // [kMaxPlanSeqs + 1]
+  int* hist = cum + kMaxPlanSeqs + 1;                                       // [132]
+  unsigned short* tail_order = reinterpret_cast<unsigned short*>(hist + 132);   // [kMaxPlanSeqs]
+  Plan plan{cum, tail_order, 0};
 
   if (lane == 0) {
     for (int s = 0; s < S; ++s) mbar_init(bars + 8 * s, 1);
@@ -506,12 +528,18 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   const int part_tokens = p.part_blocks * BS;
   int total_items;
   if (p.use_plan) {
-    // partition plan: exclusive prefix sums of the per-sequence partition counts (every CTA
-    // builds its own copy: num_seqs <= 2048 integers).  All threads fetch the context lengths
-    // at once (one L2 round trip), warp 0 scans them out of shared memory.
+    // partition plan (every CTA builds its own copy; num_seqs <= 1024): prefix sums of the FULL
+    // partitions per sequence, and the sequences with a partial last partition counting-sorted
+    // by its length, longest first.  All threads fetch the context lengths at once (one L2
+    // round trip); everything else runs out of shared memory.
+    for (int i = threadIdx.x; i < 132; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
     for (int s = threadIdx.x; s < p.num_seqs; s += blockDim.x) {
       const int c = p.context_lens[s];
-      cum[s + 1] = c > 0 ? (c + part_tokens - 1) / part_tokens : 1;   // empty context: one item writes zeros
+      cum[s + 1] = c / part_tokens;
+      const int rem = c % part_tokens;
+      if (rem != 0 || c == 0)           // empty context: a zero-tile tail item writes zeros
+        atomicAdd(&hist[(rem + BS - 1) / BS], 1);
     }
     __syncthreads();
     if (warp == 0) {
@@ -529,10 +557,28 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         if (s < p.num_seqs) cum[s + 1] = carry + incl;
         carry += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) cum[0] = 0;
+      if (lane == 0) {
+        cum[0] = 0;
+        int run = 0;                    // descending bucket offsets
+        for (int b = 65; b >= 0; --b) {
+          hist[66 + b] = run;
+          run += hist[b];
+        }
+      }
     }
     __syncthreads();
-    total_items = cum[p.num_seqs] * p.passes * p.num_kv_heads;
+    const int n_tail = hist[0] + hist[66 + 0];   // offset of the last bucket + its count
+    for (int s = threadIdx.x; s < p.num_seqs; s += blockDim.x) {
+      const int c = p.context_lens[s];          // L1 hit: read a moment ago
+      const int rem = c % part_tokens;
+      if (rem != 0 || c == 0)
+        tail_order[atomicAdd(&hist[66 + (rem + BS - 1) / BS], 1)] = (unsigned short)s;
+    }
+    __syncthreads();
+    plan.cum = cum;
+    plan.tail_order = tail_order;
+    plan.n_full = cum[p.num_seqs];
+    total_items = (plan.n_full + n_tail) * p.passes * p.num_kv_heads;
   } else {
     __syncwarp();
     total_items = p.num_seqs * p.n_part * p.passes * p.num_kv_heads;
@@ -581,12 +627,12 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   nxt.valid = 0;
   int pend = fetch_id(p, lane);
   bool pend_valid = false, nxt_ready = false;
-  claim(cur, pend, p, cum, total_items, part_tokens, BS, lane);
+  claim(cur, pend, p, plan, total_items, part_tokens, BS, lane);
   pump(cur);
   auto advance = [&]() {
     if (!nxt_ready) {
       if (!pend_valid) pend = fetch_id(p, lane);
-      claim(nxt, pend, p, cum, total_items, part_tokens, BS, lane);
+      claim(nxt, pend, p, plan, total_items, part_tokens, BS, lane);
     }
     cur = nxt;
     nxt.valid = 0;
@@ -681,7 +727,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         pend = fetch_id(p, lane);
         pend_valid = true;
       } else if (pend_valid && !nxt_ready && cur.issued >= ntiles) {
-        claim(nxt, pend, p, cum, total_items, part_tokens, BS, lane);
+        claim(nxt, pend, p, plan, total_items, part_tokens, BS, lane);
         nxt_ready = true;
         pend_valid = false;
         pump(nxt);

@@ -32,7 +32,7 @@ constexpr int kMaxWorld = 8;
 constexpr int kPadBase = 1024;         // our flags start here (u32 index); torch's own barrier uses the front
 constexpr int kThreads = 256;
 // signal-pad layout (u32 index from kPadBase): [0..7] arrival epoch of rank p (written by p),
-// [8] local "go" epoch (CTA 0 -> the other CTAs of this rank), [9] local count of finished CTAs
+// [9] local count of finished CTAs
 
 struct Comm {
   const void* x[kMaxWorld];            // every rank's x buffer (index = rank)
@@ -64,14 +64,16 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   return v;
 }
 
-// All ranks meet: every rank writes `epoch` into its slot of every peer's pad (one-way NVLink
-// stores, no round trips) and waits until all slots of its own pad have reached `epoch`.
-// Epochs grow monotonically, so flags never need resetting.  Called by ONE CTA per rank.
-__device__ __forceinline__ void peer_barrier(const Comm& c, uint32_t epoch) {
+// Ranks meet through epoch flags: a rank ANNOUNCES by writing `epoch` into its slot of every
+// peer's pad (one-way NVLink stores, no round trips; release: everything this rank wrote before
+// is visible first), and WAITS by polling its own pad until every slot has reached `epoch`.
+// Epochs grow monotonically, so flags never need resetting.
+__device__ __forceinline__ void announce(const Comm& c, uint32_t epoch) {   // one CTA per rank
+  if (threadIdx.x < c.world) st_release_sys(c.pad[threadIdx.x] + kPadBase + c.rank, epoch);
+}
+__device__ __forceinline__ void wait_peers(const Comm& c, uint32_t epoch) {  // any CTA
   if (threadIdx.x < c.world) {
-    const int peer = threadIdx.x;
-    st_release_sys(c.pad[peer] + kPadBase + c.rank, epoch);
-    const uint32_t* mine = c.pad[c.rank] + kPadBase + peer;
+    const uint32_t* mine = c.pad[c.rank] + kPadBase + threadIdx.x;
     long long spins = 0;
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0)
       if (++spins > (1ll << 30)) spin_trap();
@@ -116,22 +118,12 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ float red[32];
   const int cta = blockIdx.x;
   const int nvec = hidden / N;
-  uint32_t* go = c.pad[c.rank] + kPadBase + 8;
   uint32_t* fin = c.pad[c.rank] + kPadBase + 9;
 
   // start: every rank's x is complete (its producing kernels finished before this one started).
-  // CTA 0 meets the peers and releases the other CTAs of this rank.
-  if (cta == 0) {
-    peer_barrier(c, c.epoch);
-    if (threadIdx.x == 0) st_release_gpu(go, c.epoch);
-  } else {
-    if (threadIdx.x == 0) {
-      long long spins = 0;
-      while ((int32_t)(ld_acquire_gpu(go) - c.epoch) < 0)
-        if (++spins > (1ll << 30)) spin_trap();
-    }
-    __syncthreads();
-  }
+  // CTA 0 announces this rank; every CTA polls the local pad for all peers' announcements.
+  if (cta == 0) announce(c, c.epoch);
+  wait_peers(c, c.epoch);
 
   // rows owned by this rank: r, r + world, ...; CTAs of this rank stride over them
   for (int row = c.rank + cta * c.world; row < num_tokens; row += gridDim.x * c.world) {
@@ -216,18 +208,22 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
   }
-  // end: all rows of all ranks have landed everywhere.  The last CTA of this rank to finish
-  // its peer stores meets the peers.
-  __threadfence_system();
+  // end: all rows of all ranks have landed everywhere.  The last CTA of this rank to finish its
+  // peer stores announces (one system-scope release by one thread covers the CTA's stores: the
+  // CTA barrier orders them before it) and waits for the peers.
   __syncthreads();
   __shared__ int s_last;
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const uint32_t done = atomicAdd(fin, 1u);
     s_last = done == gridDim.x - 1;
     if (s_last) *fin = 0u;
   }
   __syncthreads();
-  if (s_last) peer_barrier(c, c.epoch + 1);
+  if (s_last) {
+    announce(c, c.epoch + 1);
+    wait_peers(c, c.epoch + 1);
+  }
 }
 
 template <typename T, bool NORM>

@@ -568,11 +568,30 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     }
     __syncthreads();
     const int n_tail = hist[0] + hist[66 + 0];   // offset of the last bucket + its count
-    for (int s = threadIdx.x; s < p.num_seqs; s += blockDim.x) {
-      const int c = p.context_lens[s];          // L1 hit: read a moment ago
-      const int rem = c % part_tokens;
-      if (rem != 0 || c == 0)
-        tail_order[atomicAdd(&hist[66 + (rem + BS - 1) / BS], 1)] = (unsigned short)s;
+    __syncthreads();
+    // stable scatter (sequence order inside a bucket): every CTA must build the SAME order, so
+    // no atomics here - warp 0 walks the sequences 32 at a time and ranks equal buckets by lane
+    if (warp == 0) {
+      for (int base = 0; base < p.num_seqs; base += 32) {
+        const int s = base + lane;
+        int b = -1;
+        if (s < p.num_seqs) {
+          const int c = p.context_lens[s];          // L1 hit: read a moment ago
+          const int rem = c % part_tokens;
+          if (rem != 0 || c == 0) b = (rem + BS - 1) / BS;
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(same) - 1;
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        int start = 0;
+        if (b >= 0 && lane == leader) {
+          start = hist[66 + b];
+          hist[66 + b] = start + __popc(same);
+        }
+        start = __shfl_sync(0xffffffffu, start, leader);
+        if (b >= 0) tail_order[start + rank] = (unsigned short)s;
+        __syncwarp();
+      }
     }
     __syncthreads();
     plan.cum = cum;

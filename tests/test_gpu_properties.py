@@ -80,7 +80,10 @@ def test_attention_properties_full_size(C, hq, hkv, dtype, kv):
     assert torch.allclose(base.float(), _attn(C, c, "v2").float(), atol=tol, rtol=1e-5)
     # (4) exact linearity in V under power-of-two scaling (2-byte caches: exponent shift)
     if kv == "auto":
-        assert torch.equal((_attn(C, c, vc=c["vc"] * 2)).float(), base.float() * 2)
+        doubled = _attn(C, c, vc=c["vc"] * 2).float()
+        normal = base.float().abs() >= 2.0 ** -13      # f16 subnormal results round on another grid
+        assert torch.equal(doubled[normal], (base.float() * 2)[normal])
+        assert torch.allclose(doubled, base.float() * 2, atol=2.0 ** -23, rtol=0)
     # (5) a convex combination of V rows: every output lies inside the value range
     lo, hi = -128 ** -0.5, 128 ** -0.5
     if kv == "auto":

@@ -214,6 +214,47 @@ def main():
         ours = timeit(lambda: _C.cache_ops.copy_blocks(ks, vs, mapping), iters=10)
         rr = timeit(lambda: ref.cache_ops.copy_blocks(ks, vs, mapping), iters=10) if ref else None
         report("copy_blocks", "32 layers x 64 pairs x 128 KiB", byts, ours, rr)
+    if "gemm" in ops_sel:
+        # the predictor's dense layers: ours (tcgen05) next to cuBLAS (torch.nn.functional.linear)
+        from vllm_ltr_b200 import predictor as P
+        for M in (245, 2048):
+            for N, K, relu, resid in ((2304, 768, False, False), (768, 768, False, True),
+                                      (3072, 768, True, False), (768, 3072, False, True),
+                                      (4096, 1024, True, False), (1024, 4096, False, True)):
+                a = torch.randn(M, K, generator=g, device=DEV).half()
+                w = (torch.randn(N, K, generator=g, device=DEV) * 0.05).half()
+                b = torch.randn(N, generator=g, device=DEV).half()
+                r = torch.randn(M, N, generator=g, device=DEV).half() if resid else None
+                ours = timeit(lambda: P.gemm(a, w, bias=b, resid=r, relu=relu), flush=False)
+
+                def cublas():
+                    y = torch.nn.functional.linear(a, w, b)
+                    if relu:
+                        y = torch.relu(y)
+                    if r is not None:
+                        y = y + r
+                    return y
+                rr = timeit(cublas, flush=False)
+                fl = 2.0 * M * N * K
+                print(f"gemm       M={M} N={N} K={K} relu={int(relu)} resid={int(resid)}  ours {ours*1e3:8.1f} us "
+                      f"{fl/ours/1e9:7.1f} TFLOP/s   cuBLAS+epilogue {rr*1e3:8.1f} us {fl/rr/1e9:7.1f} TFLOP/s  x{rr/ours:.2f}",
+                      flush=True)
+                rows.append(dict(op="gemm", shape=f"M={M} N={N} K={K}", ours_ms=ours, ref_ms=rr,
+                                 tflops=fl / ours / 1e9))
+    if "predictor" in ops_sel:
+        from vllm_ltr_b200 import predictor as P
+        for kind in ("125m", "350m"):
+            cfg, sd = P.dummy_checkpoint(kind)
+            pred = P.OPTPredictor(cfg, sd, device=DEV)
+            rng = np.random.default_rng(0)
+            for desc, lens in (("1x245", [245]), ("8x256", [256] * 8), ("1x2048", [2048]),
+                               ("14x~146", [146] * 14)):
+                prompts = [rng.integers(1000, 49000, L).tolist() for L in lens]
+                ms = timeit(lambda: pred.logits(prompts), iters=10, flush=False)
+                toks = sum(lens)
+                print(f"predictor  opt-{kind} prompts={desc} tokens={toks}  {ms*1e3:9.1f} us  "
+                      f"{toks/ms/1e3:8.1f} Mtok/s", flush=True)
+                rows.append(dict(op="predictor", shape=f"{kind} {desc}", ours_ms=ms))
     if args.json:
         json.dump(rows, open(args.json, "w"), indent=1)
 

@@ -75,6 +75,27 @@ int vltr_paged_attention_v2(void* out, float* exp_sums, float* max_logits, void*
                             int64_t q_stride, int64_t kv_block_stride, int64_t kv_head_stride,
                             int dtype, int kv_fp8, float kv_scale, void* stream);
 
+/* ---- prefill attention over the paged cache ("prefix prefill") ---------------------------------
+ * Replaces the Triton kernel context_attention_fwd (vllm/attention/ops/prefix_prefill.py:630-755;
+ * kernels :10-628), which the reference runs for every prefill chunk under chunked prefill
+ * (PagedAttention.forward_prefix, vllm/attention/ops/paged_attn.py:163-195).
+ *   query/out [num_tokens, num_heads, head_size], key/value [num_tokens, num_kv_heads, head_size]
+ *   (row strides in elements); sequence b owns rows start_loc[b] .. + (seq_lens[b] - ctx_lens[b]);
+ *   its first ctx_lens[b] tokens are already in the paged cache (layouts as for paged_attention).
+ *   out[i] = softmax(scale * q[i] . K(0 .. ctx + i)) . V(0 .. ctx + i), ALiBi optional.
+ * The kernel reads ALL keys from the cache.  cache_has_new_tokens = 1: the caller has already
+ * written the chunk's key/value into their slots (the engine does, flash_attn.py:192);
+ * 0: the op writes them first (key/value must be given).  dtype VLTR_F16 / VLTR_BF16. */
+int vltr_context_attention_fwd(void* out, const void* query, const void* key, const void* value,
+                               void* key_cache, void* value_cache, const int32_t* block_tables,
+                               const int32_t* start_loc, const int32_t* seq_lens,
+                               const int32_t* ctx_lens, int num_seqs, int num_tokens,
+                               int num_heads, int num_kv_heads, int head_size, int block_size,
+                               int max_num_blocks_per_seq, float scale, const float* alibi_slopes,
+                               int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                               int64_t o_stride, int64_t kv_block_stride, int64_t kv_head_stride,
+                               int dtype, int kv_fp8, int cache_has_new_tokens, void* stream);
+
 /* ---- cache ops: csrc/cache_kernels.cu ------------------------------------------------------
  * reshape_and_cache (:235-276): key/value [num_tokens, num_heads, head_size] with row strides
  * key_stride/value_stride (elements); slot_mapping [num_tokens] int64, slot < 0 skipped. */

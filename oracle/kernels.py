@@ -316,6 +316,49 @@ def paged_attention_partitions(query: torch.Tensor, key_cache: torch.Tensor,
     return ml, es, to
 
 
+def context_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_cache: torch.Tensor,
+                      value_cache: torch.Tensor, block_tables: torch.Tensor,
+                      start_loc: torch.Tensor, seq_lens: torch.Tensor, ctx_lens: torch.Tensor,
+                      alibi_slopes: Optional[torch.Tensor] = None,
+                      kv_cache_dtype: str = "auto") -> torch.Tensor:
+    """Prefill attention with a cached prefix (vllm/attention/ops/prefix_prefill.py:10-628; the
+    reference's own test oracle, tests/kernels/test_prefix_prefill.py:60-170, is the same maths
+    with xformers' BlockDiagonalCausalFromBottomRightMask): token i of sequence b attends to the
+    first ctx_b tokens of the paged cache and to chunk tokens 0..i taken from k / v.  float64;
+    returns float32 [num_tokens, Hq, D]."""
+    T, Hq, D = q.shape
+    Hkv = k.shape[1]
+    G = Hq // Hkv
+    nb, _, Dx, bs, x = key_cache.shape
+    dev = q.device
+    out = torch.zeros(T, Hq, D, dtype=torch.float32, device=dev)
+    if kv_cache_dtype == "fp8":
+        key_cache = fp8_e5m2_to(key_cache, torch.float32)
+        value_cache = fp8_e5m2_to(value_cache, torch.float32)
+    scale = D ** -0.5
+    for b in range(seq_lens.shape[0]):
+        c, n = int(ctx_lens[b]), int(seq_lens[b]) - int(ctx_lens[b])
+        if n <= 0:
+            continue
+        s0 = int(start_loc[b])
+        nblk = (c + bs - 1) // bs
+        ids = block_tables[b, :nblk].to(torch.int64)
+        kp = key_cache[ids].permute(0, 3, 1, 2, 4).reshape(nblk * bs, Hkv, D)[:c].to(torch.float64)
+        vp = value_cache[ids].permute(0, 3, 1, 2).reshape(nblk * bs, Hkv, D)[:c].to(torch.float64)
+        kk = torch.cat([kp, k[s0:s0 + n].to(torch.float64)]).repeat_interleave(G, dim=1)
+        vv = torch.cat([vp, v[s0:s0 + n].to(torch.float64)]).repeat_interleave(G, dim=1)
+        logits = scale * torch.einsum("qhd,khd->hqk", q[s0:s0 + n].to(torch.float64), kk)
+        qpos = c + torch.arange(n, device=dev)
+        kpos = torch.arange(c + n, device=dev)
+        if alibi_slopes is not None:
+            logits = logits + alibi_slopes.to(torch.float64)[:, None, None] * \
+                (kpos[None, None, :] - qpos[None, :, None]).to(torch.float64)
+        logits = logits.masked_fill(kpos[None, None, :] > qpos[None, :, None], float("-inf"))
+        p = torch.softmax(logits, dim=-1)
+        out[s0:s0 + n] = torch.einsum("hqk,khd->qhd", p, vv).to(torch.float32)
+    return out
+
+
 def make_kv_cache(num_blocks: int, block_size: int, num_kv_heads: int, head_size: int,
                   dtype: torch.dtype, seed: int, kv_cache_dtype: str = "auto"):
     """Random caches in the paged layout, uniform(-1/sqrt(D), 1/sqrt(D)) like the reference fixture

@@ -1,0 +1,126 @@
+"""GPU parity of the prefill ("prefix prefill") attention, vltr_context_attention_fwd, against the
+oracle (oracle/kernels.py:context_attention, float64).  Grid of the reference's
+tests/kernels/test_prefix_prefill.py (10 sequences, chunk and prefix lengths up to 1024, 64 query
+heads, 1 / 8 queries per kv head, head sizes 128 / 96, block 32, inputs uniform(+-1e-3), atol 1e-6)
+plus engine shapes: block 16, GQA 4, bf16, e5m2 cache, ALiBi, chunk boundaries around the block
+size, and the engine flow where the chunk is already in the cache."""
+import random
+
+import pytest
+import torch
+
+from oracle import kernels as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def fwd():
+    from vllm_ltr_b200.prefix_prefill import context_attention_fwd
+    return context_attention_fwd
+
+
+def build(num_heads, G, D, bs, dtype, sub_lens, ctx_lens, amp, seed, kv="auto", alibi=False,
+          int64_meta=False):
+    rnd = random.Random(seed)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    hkv = num_heads // G
+    B = len(sub_lens)
+    seq_lens = [a + b for a, b in zip(sub_lens, ctx_lens)]
+    T = sum(sub_lens)
+    u = lambda *s: ((torch.rand(*s, generator=g, device=DEV) * 2 - 1) * amp).to(dtype)
+    q, k, v = u(T, num_heads, D), u(T, hkv, D), u(T, hkv, D)
+    mb = max((s + bs - 1) // bs for s in seq_lens)
+    nblocks = B * mb + 7
+    perm = list(range(nblocks))
+    rnd.shuffle(perm)
+    bt = torch.tensor(perm[:B * mb], dtype=torch.int32).view(B, mb)
+    x = 16 // (1 if kv == "fp8" else 2)
+    kp, vp = u(nblocks, hkv, D // x, bs, x), u(nblocks, hkv, D, bs)     # prefix contents
+    if kv == "fp8":
+        kc, vc = K.fp8_e5m2_from_fast(kp), K.fp8_e5m2_from_fast(vp)
+    else:
+        kc, vc = kp, vp
+    meta = torch.int64 if int64_meta else torch.int32
+    start = torch.tensor([sum(sub_lens[:i]) for i in range(B)], dtype=meta, device=DEV)
+    sl = torch.tensor(seq_lens, dtype=meta, device=DEV)
+    cl = torch.tensor(ctx_lens, dtype=meta, device=DEV)
+    al = torch.randn(num_heads, generator=g, device=DEV) * 0.1 if alibi else None
+    return dict(q=q, k=k, v=v, kc=kc, vc=vc, bt=bt.to(DEV), start=start, sl=sl, cl=cl, al=al,
+                kv=kv, max_sub=max(sub_lens))
+
+
+def run_and_check(fwd, c, atol, cached=False):
+    out = torch.full_like(c["q"], float("nan"))
+    kc, vc = c["kc"].clone(), c["vc"].clone()
+    k_used, v_used = c["k"], c["v"]
+    if c["kv"] == "fp8":   # the op quantises the chunk into the cache and reads it back from there
+        k_used = K.fp8_e5m2_to(K.fp8_e5m2_from_fast(c["k"]), c["k"].dtype)
+        v_used = K.fp8_e5m2_to(K.fp8_e5m2_from_fast(c["v"]), c["v"].dtype)
+    ref = K.context_attention(c["q"], k_used, v_used, c["kc"], c["vc"], c["bt"], c["start"],
+                              c["sl"], c["cl"], c["al"], c["kv"])
+    if cached:   # engine flow: write_to_paged_cache ran first
+        from vllm_ltr_b200 import _C
+        bs = vc.shape[3]
+        slots = []
+        for b in range(c["sl"].shape[0]):
+            ctx, n = int(c["cl"][b]), int(c["sl"][b]) - int(c["cl"][b])
+            for i in range(n):
+                pos = ctx + i
+                slots.append(int(c["bt"][b, pos // bs]) * bs + pos % bs)
+        _C.cache_ops.reshape_and_cache(c["k"], c["v"], kc, vc,
+                                       torch.tensor(slots, dtype=torch.long, device=DEV),
+                                       c["kv"], 1.0)
+    fwd(c["q"], c["k"], c["v"], out, kc, vc, c["bt"], c["start"], c["sl"], c["cl"], c["max_sub"],
+        c["al"], cache_has_new_tokens=cached)
+    o = out.float()
+    assert torch.isfinite(o).all()
+    err = (o - ref).abs().max().item()
+    assert err <= atol, err
+
+
+@pytest.mark.parametrize("G", [1, 8, 16])
+@pytest.mark.parametrize("D", [128, 96])
+def test_reference_grid(fwd, G, D):
+    """tests/kernels/test_prefix_prefill.py: BS 10, lengths 16..1024, 64 heads, block 32, f16,
+    inputs uniform(+-1e-3), atol 1e-6 (64 queries per kv head is outside this kernel: G <= 16)."""
+    rnd = random.Random(0)
+    sub = [rnd.randint(16, 1024) for _ in range(10)]
+    ctx = [rnd.randint(16, 1024) for _ in range(10)]
+    c = build(64, G, D, 32, torch.float16, sub, ctx, 1e-3, 0, int64_meta=True)
+    run_and_check(fwd, c, 1e-6)
+
+
+@pytest.mark.parametrize("heads,G", [(32, 1), (32, 4), (8, 8), (12, 2), (6, 3)])
+@pytest.mark.parametrize("bs", [8, 16, 32])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kv", ["auto", "fp8"])
+def test_engine_shapes(fwd, heads, G, bs, dtype, kv):
+    """chunked-prefill shapes: chunks and prefixes around block boundaries, zero prefix (first
+    chunk), single-token chunks, a long prefix."""
+    sub = [1, bs - 1, bs, bs + 1, 17, 100, 333, 2, 64, 5]
+    ctx = [0, 0, 3, bs, 1, 700, 0, 2047, bs - 1, 4 * bs]
+    c = build(heads, G, 128, bs, dtype, sub, ctx, 0.5, 3, kv=kv, alibi=(G == 4))
+    tol = (3e-2 if kv == "fp8" else 4e-3) if dtype == torch.bfloat16 else (2e-2 if kv == "fp8" else 2e-3)
+    run_and_check(fwd, c, tol)
+    run_and_check(fwd, c, tol, cached=True)
+
+
+def test_budget_sized_step(fwd):
+    """one engine step's worth: 768 chunk tokens over 12 sequences of the trace's prompt lengths."""
+    sub = [64] * 12
+    ctx = [0, 64, 128, 192, 256, 512, 1024, 1500, 2047, 300, 77, 900]
+    c = build(32, 4, 128, 16, torch.bfloat16, sub, ctx, 0.5, 9)
+    run_and_check(fwd, c, 4e-3, cached=True)
+
+
+def test_errors(fwd):
+    c = build(8, 1, 128, 16, torch.float16, [4], [4], 0.1, 0)
+    with pytest.raises(RuntimeError, match="Unsupported data type"):
+        fwd(c["q"].float(), c["k"].float(), c["v"].float(), c["q"].float(), c["kc"], c["vc"],
+            c["bt"], c["start"], c["sl"], c["cl"], 4)
+    c32 = build(64, 32, 128, 16, torch.float16, [4], [4], 0.1, 0)
+    with pytest.raises(RuntimeError, match="max 16"):
+        fwd(c32["q"], c32["k"], c32["v"], torch.empty_like(c32["q"]), c32["kc"], c32["vc"],
+            c32["bt"], c32["start"], c32["sl"], c32["cl"], 4)

@@ -219,3 +219,40 @@ def test_partition_oracle_is_consistent_with_full_oracle():
     wgt = torch.where(live, es * torch.exp(mlz - gm), torch.zeros_like(es))
     merged = (torch.nan_to_num(tmp) * (wgt / (wgt.sum(-1, keepdim=True) + 1e-6))[..., None]).sum(2)
     assert torch.allclose(merged, full, atol=1e-5, rtol=1e-4)
+
+
+# ---- 5. prefill attention oracle vs torch SDPA (independent formulation) ------------------------
+def test_context_attention_oracle_matches_sdpa():
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    Hq, Hkv, D, bs = 8, 2, 64, 16
+    sub, ctx = [5, 33, 1], [0, 40, 17]
+    seq = [a + b for a, b in zip(sub, ctx)]
+    T = sum(sub)
+    q = torch.randn(T, Hq, D, generator=g)
+    k, v = torch.randn(T, Hkv, D, generator=g), torch.randn(T, Hkv, D, generator=g)
+    full_k = [torch.randn(s, Hkv, D, generator=g) for s in seq]
+    full_v = [torch.randn(s, Hkv, D, generator=g) for s in seq]
+    mb = max((s + bs - 1) // bs for s in seq)
+    nb = 3 * mb
+    kc = torch.zeros(nb, Hkv, D // 4, bs, 4)
+    vc = torch.zeros(nb, Hkv, D, bs)
+    bt = torch.arange(nb, dtype=torch.int32).view(3, mb)
+    start = torch.tensor([0, 5, 38], dtype=torch.int32)
+    for b in range(3):
+        s0 = int(start[b])
+        full_k[b][ctx[b]:] = k[s0:s0 + sub[b]]
+        full_v[b][ctx[b]:] = v[s0:s0 + sub[b]]
+        for pos in range(ctx[b]):
+            blk, off = int(bt[b, pos // bs]), pos % bs
+            kc[blk, :, :, off, :] = full_k[b][pos].view(Hkv, D // 4, 4)
+            vc[blk, :, :, off] = full_v[b][pos]
+    out = K.context_attention(q, k, v, kc, vc, bt, start, torch.tensor(seq), torch.tensor(ctx))
+    for b in range(3):
+        s0, n, c = int(start[b]), sub[b], ctx[b]
+        qq = q[s0:s0 + n].transpose(0, 1)                                   # [Hq, n, D]
+        kk = full_k[b].repeat_interleave(Hq // Hkv, dim=1).transpose(0, 1)  # [Hq, S, D]
+        vv = full_v[b].repeat_interleave(Hq // Hkv, dim=1).transpose(0, 1)
+        mask = torch.arange(c + n)[None, :] <= (c + torch.arange(n))[:, None]
+        ref = F.scaled_dot_product_attention(qq, kk, vv, attn_mask=mask).transpose(0, 1)
+        assert torch.allclose(out[s0:s0 + n], ref, atol=1e-5, rtol=1e-4)

@@ -62,7 +62,9 @@ struct Params {
   int num_seqs, num_heads, num_kv_heads, group, passes;
   int max_blocks_per_seq;
   int n_part;                   // partitions of the longest context (second-to-last tmp dim)
-  int part_blocks;              // KV blocks per partition (<= 64)
+  int part_blocks;              // KV blocks per partition (<= 64); the MINIMUM when `adaptive`
+  int adaptive;                 // v1 + plan: the kernel sizes partitions from the actual contexts
+  int part_blocks_cap;          // adaptive: largest partition (KV blocks)
   float scale;
   int64_t q_stride;             // elements
   int64_t kv_block_stride;      // bytes
@@ -443,8 +445,9 @@ struct Plan {
   int n_full;                       // total number of full partitions
 };
 __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p, const Plan& plan,
-                                      int total_items, int part_tokens, int BS, int lane) {
+                                      int total_items, int part_blocks, int BS, int lane) {
   const int* cum = plan.cum;
+  const int part_tokens = part_blocks * BS;
   const int item = __shfl_sync(0xffffffffu, pending_id, 0);
   it.valid = item < total_items;
   it.issued = 0;
@@ -479,17 +482,17 @@ __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p,
     it.ctx = p.context_lens[it.seq];
     it.part = it.ctx / part_tokens;
   }
-  it.blk0 = it.part * p.part_blocks;
+  it.blk0 = it.part * part_blocks;
   // block ids and the context length are independent loads (one L2 round trip, not two): the
   // table row is read up to its allocated width and masked by the context afterwards
   const int32_t* bt = p.block_tables + (int64_t)it.seq * p.max_blocks_per_seq + it.blk0;
-  const int room = min(p.part_blocks, p.max_blocks_per_seq - it.blk0);
+  const int room = min(part_blocks, p.max_blocks_per_seq - it.blk0);
   const int b0 = lane < room ? bt[lane] : 0;
   const int b1 = 32 + lane < room ? bt[32 + lane] : 0;
   it.ctx = p.context_lens[it.seq];
   const int nblk_ctx = (it.ctx + BS - 1) / BS;
   it.nparts = (it.ctx + part_tokens - 1) / part_tokens;
-  const int blk1 = min(it.blk0 + p.part_blocks, nblk_ctx);
+  const int blk1 = min(it.blk0 + part_blocks, nblk_ctx);
   it.ntiles = max(blk1 - it.blk0, 0);
   it.bt0 = lane < it.ntiles ? b0 : 0;
   it.bt1 = 32 + lane < it.ntiles ? b1 : 0;
@@ -525,9 +528,32 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     for (int s = 0; s < S; ++s) mbar_init(bars + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const int part_tokens = p.part_blocks * BS;
+  int part_blocks = p.part_blocks;
+  int part_tokens = part_blocks * BS;
   int total_items;
   if (p.use_plan) {
+    if (p.adaptive) {
+      // size the partitions from the ACTUAL contexts (the host only knows the maximum): about
+      // 1.5 work items per resident warp, between the host's minimum and cap.  Every CTA
+      // computes the same value (integer arithmetic on the same inputs).
+      if (threadIdx.x == 0) hist[131] = 0;
+      __syncthreads();
+      int mine = 0;
+      for (int s = threadIdx.x; s < p.num_seqs; s += blockDim.x)
+        mine += (p.context_lens[s] + BS - 1) / BS;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+      if (lane == 0 && mine != 0) atomicAdd(&hist[131], mine);
+      __syncthreads();
+      const long long tiles = (long long)hist[131] * p.num_kv_heads * p.passes;
+      const long long want_items = ((long long)gridDim.x * nwarps * 3) / 2;
+      long long pb = (tiles + want_items - 1) / want_items;
+      if (pb < p.part_blocks) pb = p.part_blocks;
+      if (pb > p.part_blocks_cap) pb = p.part_blocks_cap;
+      part_blocks = (int)pb;
+      part_tokens = part_blocks * BS;
+      __syncthreads();
+    }
     // partition plan (every CTA builds its own copy; num_seqs <= 1024): prefix sums of the FULL
     // partitions per sequence, and the sequences with a partial last partition counting-sorted
     // by its length, longest first.  All threads fetch the context lengths at once (one L2
@@ -646,12 +672,12 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   nxt.valid = 0;
   int pend = fetch_id(p, lane);
   bool pend_valid = false, nxt_ready = false;
-  claim(cur, pend, p, plan, total_items, part_tokens, BS, lane);
+  claim(cur, pend, p, plan, total_items, part_blocks, BS, lane);
   pump(cur);
   auto advance = [&]() {
     if (!nxt_ready) {
       if (!pend_valid) pend = fetch_id(p, lane);
-      claim(nxt, pend, p, plan, total_items, part_tokens, BS, lane);
+      claim(nxt, pend, p, plan, total_items, part_blocks, BS, lane);
     }
     cur = nxt;
     nxt.valid = 0;
@@ -746,7 +772,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         pend = fetch_id(p, lane);
         pend_valid = true;
       } else if (pend_valid && !nxt_ready && cur.issued >= ntiles) {
-        claim(nxt, pend, p, plan, total_items, part_tokens, BS, lane);
+        claim(nxt, pend, p, plan, total_items, part_blocks, BS, lane);
         nxt_ready = true;
         pend_valid = false;
         pump(nxt);

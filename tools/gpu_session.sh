@@ -22,6 +22,7 @@ for s in $STEPS; do
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 3 -c 1 -f -o $OUT/attn_tp8_prof python tools/op_sweep.py --ops attn --only 70b-tp8-bf16:256:512:v1 > $OUT/ncutp8.log 2>&1; echo "ncutp8 rc=$?"; tail -3 $OUT/ncutp8.log ;;
     sweeppred) timeout 600 python tools/op_sweep.py --ops gemm,predictor --json $OUT/sweep_pred.json > $OUT/sweep_pred.log 2>&1; echo "sweeppred rc=$?"; cat $OUT/sweep_pred.log ;;
     ncugemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 20 -c 3 -f -o $OUT/gemm_prof python tools/op_sweep.py --ops gemm > $OUT/ncugemm.log 2>&1; echo "ncugemm rc=$?"; tail -3 $OUT/ncugemm.log ;;
+    prefilltests) timeout 900 python -m pytest tests/test_gpu_prefill.py tests/test_gpu_properties.py -q --maxfail=20 -p no:cacheprovider > $OUT/prefilltests.log 2>&1; echo "prefilltests rc=$?"; tail -25 $OUT/prefilltests.log ;;
     golden)  timeout 600 python tests/golden/gen_golden_cuda.py $OUT/ref_cuda.npz > $OUT/golden.log 2>&1; echo "golden rc=$?"; tail -2 $OUT/golden.log ;;
     bench)   timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "benchref rc=$?"; cat $OUT/bench_ref.json ;;

@@ -176,22 +176,11 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     if (pb > 64) pb = 64;
     p.part_blocks = pb;
     p.n_part = max_blocks > 0 ? (max_blocks + pb - 1) / pb : 1;
-    if (p.use_plan) {
-      // the kernel picks the partition size itself from the actual context lengths; the host
-      // fixes the range: at least 64 tokens and at most 64 partitions per sequence (this also
-      // sizes the partial workspace), at most min(512 tokens, 64 blocks)
-      int pb_min = (64 + block_size - 1) / block_size;
-      const int by_count = (max_blocks + 63) / 64;
-      if (pb_min < by_count) pb_min = by_count;
-      if (pb_min > 64) pb_min = 64;
-      int pb_cap = 512 / block_size;
-      if (pb_cap < pb_min) pb_cap = pb_min;
-      if (pb_cap > 64) pb_cap = 64;
-      p.adaptive = 1;
-      p.part_blocks = pb_min;
-      p.part_blocks_cap = pb_cap;
-      p.n_part = max_blocks > 0 ? (max_blocks + pb_min - 1) / pb_min : 1;
-    }
+    // (The kernel can also size partitions itself from the actual contexts - Params::adaptive.
+    // Measured on B200 it loses to this host policy: finer partitions cost more in per-item
+    // set-up and merging than they win in balance, see profiles/r01_op_sweep_adaptive.txt.)
+    p.adaptive = 0;
+    p.part_blocks_cap = pb;
     p.always_partial = 0;
     p.tmp_is_f32 = 1;
     if (p.n_part > 1) {

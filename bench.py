@@ -362,6 +362,11 @@ def _main(out):
     ap.add_argument("--cpu-sample-batch", type=int, default=256)
     ap.add_argument("--tp-exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused peer-memory all-reduce+norm kernel, or NCCL all_reduce + norm")
+    ap.add_argument("--e2e-launch", default="graph", choices=["graph", "eager"],
+                    help="N=1 e2e leg: replay the step from a CUDA graph (default) or issue it "
+                         "kernel by kernel")
+    ap.add_argument("--no-pdl", action="store_true",
+                    help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-tick", dest="tick", action="store_false",
                     help="leave the LTR scheduling tick (a8, a10) out of the step")
     ap.add_argument("--live-requests", type=int, default=10000,
@@ -417,8 +422,10 @@ def _main(out):
     # ---------------- our arm ----------------
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     import torch.distributed as dist
-    from vllm_ltr_b200._lib import launch_count
+    from vllm_ltr_b200._lib import launch_count, tune
     from vllm_ltr_b200.hotpath import DecodeHotPath
+    if args.no_pdl:
+        tune("pdl", 0)
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
@@ -458,10 +465,26 @@ def _main(out):
             tick()
         return out
 
+    # e2e leg at N=1: the step is recorded once into a CUDA graph over static device inputs; per
+    # step the host buffers are copied into them, the graph is replayed and the result read back
+    use_graph = world == 1 and args.e2e_launch == "graph"
+    graph = graph_out = None
+    if use_graph:
+        n_before = launch_count()
+        graph, graph_out = hp.capture(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                                      devin["block_tables"], devin["context_lens"], max_ctx)
+        launches_per_graph = (launch_count() - n_before) // 2     # warm-up step + recorded step
+
     def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        out = hp.step(d["hidden"], d["positions"], d["slot_mapping"], d["block_tables"],
-                      d["context_lens"], max_ctx, all_reduce)
+        if use_graph:
+            for k, v in pinned.items():
+                devin[k].copy_(v, non_blocking=True)
+            graph.replay()
+            out = graph_out
+        else:
+            d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            out = hp.step(d["hidden"], d["positions"], d["slot_mapping"], d["block_tables"],
+                          d["context_lens"], max_ctx, all_reduce)
         out_host.copy_(out, non_blocking=True)
         if tick:
             tick()
@@ -563,7 +586,10 @@ def _main(out):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": config, "clocks": clk,
         "e2e": {"value": e2e_tps, "unit": "tokens/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                "launch": ("cuda graph replay (%d kernels per step)" % launches_per_graph
+                           if use_graph else "eager")},
+        "pdl": not args.no_pdl,
         "gpu_launches": int(launches), "roofline": roofline,
         "host_issue_ms_per_step": host_ms, "tick_ms_alone": tick_ms,
     }

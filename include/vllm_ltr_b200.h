@@ -45,6 +45,11 @@ const char* vltr_last_error(void);
 const char* vltr_build_info(void);
 /* number of kernel launches issued through this library since load (process-wide). */
 uint64_t vltr_launch_count(void);
+/* development knobs, not part of the reference surface.  "pdl" 0/1: launch the hot-path kernels
+ * with programmatic dependent launch (default 1, env VLTR_PDL); "attn_warps", "attn_stages",
+ * "attn_ctas", "attn_slots", "attn_cap_tokens", "attn_min_tokens": override the paged-attention
+ * launch policy (0 = default); "attn_trace": device pointer receiving per-warp timestamps. */
+int vltr_tune(const char* key, long long value);
 
 /* ---- attention: csrc/attention/attention_kernels.cu:741-778 (v1), :935-975 (v2) ------------
  * out   [num_seqs, num_heads, head_size]            (contiguous)

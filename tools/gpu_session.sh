@@ -23,6 +23,11 @@ for s in $STEPS; do
     sweeppred) timeout 600 python tools/op_sweep.py --ops gemm,predictor --json $OUT/sweep_pred.json > $OUT/sweep_pred.log 2>&1; echo "sweeppred rc=$?"; cat $OUT/sweep_pred.log ;;
     ncugemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 20 -c 3 -f -o $OUT/gemm_prof python tools/op_sweep.py --ops gemm > $OUT/ncugemm.log 2>&1; echo "ncugemm rc=$?"; tail -3 $OUT/ncugemm.log ;;
     prefilltests) timeout 900 python -m pytest tests/test_gpu_prefill.py tests/test_gpu_properties.py -q --maxfail=20 -p no:cacheprovider > $OUT/prefilltests.log 2>&1; echo "prefilltests rc=$?"; tail -25 $OUT/prefilltests.log ;;
+    hotpathtests) timeout 600 python -m pytest tests/test_gpu_hotpath.py -q -p no:cacheprovider > $OUT/hotpathtests.log 2>&1; echo "hotpathtests rc=$?"; tail -15 $OUT/hotpathtests.log ;;
+    tune)    timeout 900 python tools/attn_tune.py --grid wide --trace --ref --json $OUT/attn_tune.json > $OUT/attn_tune.log 2>&1; echo "tune rc=$?"; cat $OUT/attn_tune.log ;;
+    tuneq)   timeout 600 python tools/attn_tune.py --trace --json $OUT/attn_tuneq.json > $OUT/attn_tuneq.log 2>&1; echo "tuneq rc=$?"; cat $OUT/attn_tuneq.log ;;
+    benchab) timeout 600 python bench.py --no-pdl --e2e-launch eager --no-cpu-baseline > $OUT/bench_nopdl_eager.json 2> $OUT/bench_ab.err; echo "benchab rc=$?"; cat $OUT/bench_nopdl_eager.json ;;
+    benchmodels) for m in llama-3-8b llama-3-8b-fp8kv; do timeout 600 python bench.py --model $m --no-cpu-baseline > $OUT/bench_$m.json 2> $OUT/bench_$m.err; echo "bench $m rc=$?"; cat $OUT/bench_$m.json; done ;;
     golden)  timeout 600 python tests/golden/gen_golden_cuda.py $OUT/ref_cuda.npz > $OUT/golden.log 2>&1; echo "golden rc=$?"; tail -2 $OUT/golden.log ;;
     bench)   timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "benchref rc=$?"; cat $OUT/bench_ref.json ;;

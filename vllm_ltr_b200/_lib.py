@@ -22,6 +22,7 @@ _SIGS = {
     "vltr_last_error": (c_char_p, []),
     "vltr_build_info": (c_char_p, []),
     "vltr_launch_count": (c_uint64, []),
+    "vltr_tune": (c_int, [c_char_p, ctypes.c_longlong]),
     "vltr_paged_attention_v1": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P,
                                         c_int, c_int, c_int, _P, c_int64, c_int64, c_int64, c_int,
                                         c_int, c_float, _P]),
@@ -73,3 +74,8 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(lib.vltr_launch_count())
+
+
+def tune(key: str, value: int) -> None:
+    """Development knobs of the library (include/vllm_ltr_b200.h: vltr_tune)."""
+    check(lib.vltr_tune(key.encode(), int(value)))

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) act_vec_kernel(T* __restrict__ out,
                                                       const T* __restrict__ input,
                                                       int64_t num_vec, int vec_per_row, int d) {
   constexpr int N = Vec16<T>::N;
+  pdl_wait();
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= num_vec) return;
   const int64_t row = i / vec_per_row;
@@ -106,8 +108,8 @@ int launch_act(void* out, const void* input, int64_t num_tokens, int d, cudaStre
     const int vec_per_row = d / N;
     const int64_t num_vec = num_tokens * vec_per_row;
     const int64_t grid = (num_vec + 255) / 256;
-    act_vec_kernel<T, ACT, GATED><<<(unsigned)grid, 256, 0, stream>>>(
-        (T*)out, (const T*)input, num_vec, vec_per_row, d);
+    launch(act_vec_kernel<T, ACT, GATED>, dim3((unsigned)grid), dim3(256), 0, stream, (T*)out,
+           (const T*)input, num_vec, vec_per_row, d);
   } else {
     const int64_t total = num_tokens * d;
     const int64_t grid = (total + 255) / 256;

@@ -159,16 +159,19 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     // warp one, at most 512 tokens (one lane-held window of block ids per item, and a short
     // tail), at least 64 tokens, and no more than 16 partitions per sequence (the merge of a
     // sequence is done by one warp)
-    const long long slots = (long long)num_sms() * 8;
+    const long long slots =
+        (long long)num_sms() * (g_tune.attn_slots > 0 ? g_tune.attn_slots : 8);
+    const long long floor_tokens = g_tune.attn_min_tokens > 0 ? g_tune.attn_min_tokens : 64;
+    const long long cap_tokens = g_tune.attn_cap_tokens > 0 ? g_tune.attn_cap_tokens : 512;
     const long long groups = (long long)num_seqs * num_kv_heads * p.passes;
     long long parts_wanted = (slots + groups - 1) / groups;
     if (parts_wanted < 1) parts_wanted = 1;
     long long pt = (max_context_len + parts_wanted - 1) / parts_wanted;
     const long long pt_min = (max_context_len + 15) / 16;
     if (pt < pt_min) pt = pt_min;
-    if (pt < 64) pt = 64;
+    if (pt < floor_tokens) pt = floor_tokens;
     int cap = 32 * block_size;
-    if (cap > 512) cap = 512;
+    if (cap > cap_tokens) cap = (int)cap_tokens;
     if (pt > cap && pt_min <= cap) pt = cap;
     if (pt > 64 * block_size) pt = 64 * block_size;
     int pb = (int)((pt + block_size - 1) / block_size);

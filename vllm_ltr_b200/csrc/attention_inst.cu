@@ -17,19 +17,26 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
   auto kern = paged_attention_kernel<T, CT, D, BS, GT, MMA>;
   // per-instantiation launch plan, computed once: stages, warps/CTA, CTAs/SM
   struct Plan { int stages, warps, smem, ctas_per_sm; bool ok; };
-  static Plan plan = [&]() {
+  auto make_plan = [&](int want_warps, int want_stages, int want_ctas) {
     Plan pl{0, 0, 0, 0, false};
-    int dev = 0, max_optin = 0;
+    int dev = 0, max_optin = 0, sm_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     // target two 4-warp CTAs per SM; shrink warps/CTA when tiles are too large for that
-    const int budget = (max_optin - 2048) / 2 - kPlanBytes;
-    int warps = 4, stages = 0;
-    for (; warps >= 1; warps >>= 1) {
-      const int lim = warps == 4 ? budget : max_optin - kPlanBytes;
-      for (stages = 6; stages >= 2; --stages)
-        if (warps * warp_smem_bytes<C>(stages) <= lim) break;
-      if (stages >= 2) break;
+    const int ctas = want_ctas > 0 ? want_ctas : 2;
+    int budget = sm_smem / ctas - 1024 - kPlanBytes;       // 1 KiB per CTA is reserved by the system
+    if (budget > max_optin - kPlanBytes) budget = max_optin - kPlanBytes;
+    int warps = want_warps > 0 ? want_warps : 4, stages = 0;
+    const int top = want_stages > 0 ? want_stages : 6;
+    // first choice: the wanted CTAs/SM with as many warps as fit; last resort: one CTA per SM
+    for (int pass = 0; pass < 2 && stages < 2; ++pass) {
+      const int lim = pass == 0 ? budget : max_optin - kPlanBytes;
+      for (warps = want_warps > 0 ? want_warps : 4; warps >= 1; warps >>= 1) {
+        for (stages = top; stages >= 2; --stages)
+          if (warps * warp_smem_bytes<C>(stages) <= lim) break;
+        if (stages >= 2) break;
+      }
     }
     if (warps < 1 || stages < 2) return pl;
     pl.stages = stages;
@@ -45,7 +52,19 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
     pl.ctas_per_sm = occ < 1 ? 1 : occ;
     pl.ok = true;
     return pl;
-  }();
+  };
+  static Plan dflt = make_plan(0, 0, 0);
+  const bool tuned = g_tune.attn_warps > 0 || g_tune.attn_stages > 0 || g_tune.attn_ctas > 0;
+  static bool was_tuned = false;
+  if (!tuned && was_tuned) {       // back from a development override: restore the attribute
+    dflt = make_plan(0, 0, 0);
+    was_tuned = false;
+  }
+  Plan plan = dflt;
+  if (tuned) {
+    plan = make_plan((int)g_tune.attn_warps, (int)g_tune.attn_stages, (int)g_tune.attn_ctas);
+    was_tuned = true;
+  }
   if (!plan.ok) return fail(VLTR_ERR_CUDA, "paged_attention: cannot configure shared memory");
   Params p = p0;
   p.stages = plan.stages;
@@ -54,7 +73,8 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
   const long long need = (items_ub + plan.warps - 1) / plan.warps;
   if (grid > need) grid = (int)need;
   if (grid < 1) grid = 1;
-  kern<<<grid, plan.warps * 32, plan.smem, stream>>>(p);
+  p.trace = reinterpret_cast<long long*>(g_tune.attn_trace);
+  launch(kern, dim3(grid), dim3(plan.warps * 32), (size_t)plan.smem, stream, p);
   VLTR_LAUNCH_CHECK("paged_attention");
   return VLTR_OK;
 }

@@ -73,7 +73,13 @@ struct Params {
   int use_plan;                 // 1: items enumerate only non-empty partitions (num_seqs <= kMaxPlanSeqs)
   int* counters;                // [0] next item, [1] finished warps   (self-resetting)
   int* tickets;                 // [num_seqs * passes * num_kv_heads] partition tickets, all zero
+  long long* trace;             // development: 8 stamps per warp (tools/attn_tune.py) or null
 };
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -510,6 +516,9 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int S = p.stages;
+  long long* tr = p.trace != nullptr ? p.trace + ((int64_t)blockIdx.x * nwarps + warp) * 8 : nullptr;
+  if (tr != nullptr && lane == 0) tr[0] = gtime();
+  int tr_items = 0, tr_tiles = 0;
   const int wbytes = warp_smem_bytes<C>(S);
   unsigned char* wbase = smem_raw + (size_t)warp * wbytes;
   const uint32_t tiles_s = smem_u32(wbase);                        // S x {K tile, V tile}
@@ -668,6 +677,13 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   // current item has <= S+2 tiles left, and turned into an item (context length + block ids) once
   // all tiles of the current item are in flight - late enough not to hoard work other warps could
   // take, early enough that its tiles are landing while the current item finishes.
+  // Everything above reads only step inputs (context lengths) and builds shared-memory state:
+  // with programmatic dependent launch it ran while the previous kernel (reshape_and_cache, which
+  // writes the newest token's K/V) was still draining.  From here on the queue counters, the
+  // query and the KV cache are read.
+  pdl_wait();
+  pdl_trigger();
+  if (tr != nullptr && lane == 0) tr[1] = gtime();
   Item cur, nxt;
   nxt.valid = 0;
   int pend = fetch_id(p, lane);
@@ -780,6 +796,10 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       const uint32_t ktile = tiles_s + stage_c * 2 * C::TILE_BYTES;
       const uint32_t vtile = ktile + C::TILE_BYTES;
       mbar_wait(bars + 8 * stage_c, phase_c);
+      if (tr != nullptr) {
+        if (tr_tiles == 0 && lane == 0) tr[2] = gtime();
+        ++tr_tiles;
+      }
       const int tok0 = (blk0 + tile) * BS;
       const bool last_partial = (blk0 + tile == nblk_ctx - 1) && (ctx % BS != 0);
 
@@ -1081,8 +1101,14 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       }
     }
     __syncwarp();  // q_s / p_s are rewritten by the next item
+    ++tr_items;
 
     advance();
+  }
+  if (tr != nullptr && lane == 0) {
+    tr[3] = gtime();
+    tr[4] = tr_items;
+    tr[5] = tr_tiles;
   }
 
   // self-resetting queue: the last warp to leave zeroes the counters for the next launch

@@ -54,10 +54,14 @@ __global__ void __launch_bounds__(256)
   constexpr int N = 16 / sizeof(T);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // the slot mapping is a step input (host-built, copied in before the layer loop): its load
+  // overlaps the tail of the kernel that produced key / value
+  const int64_t token = row < num_rows ? row / num_heads : 0;
+  const int64_t slot = row < num_rows ? slot_mapping[token] : -1;
+  pdl_wait();
+  pdl_trigger();
   if (row >= num_rows) return;
   const int head = (int)(row % num_heads);
-  const int64_t token = row / num_heads;
-  const int64_t slot = slot_mapping[token];
   if (slot < 0) return;  // padding token (cache_kernels.cu:172-175)
   const int64_t blk = slot / block_size;
   const int off = (int)(slot % block_size);
@@ -121,9 +125,9 @@ int launch_reshape(const void* key, const void* value, void* key_cache, void* va
                       (uintptr_t)value % 16 == 0 && (uintptr_t)key_cache % 16 == 0;
   if (vec_ok) {
     const int64_t rows = (int64_t)num_tokens * num_heads;
-    reshape_and_cache_vec_kernel<T, CT, FP8><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
-        (const T*)key, (const T*)value, (CT*)key_cache, (CT*)value_cache, slot_mapping,
-        key_stride, value_stride, num_heads, head_size, block_size, rows);
+    launch(reshape_and_cache_vec_kernel<T, CT, FP8>, dim3((unsigned)((rows + 7) / 8)), dim3(256),
+           0, stream, (const T*)key, (const T*)value, (CT*)key_cache, (CT*)value_cache,
+           slot_mapping, key_stride, value_stride, num_heads, head_size, block_size, rows);
   } else {
     const int64_t items = (int64_t)num_tokens * num_heads * head_size;
     reshape_and_cache_scalar_kernel<T, CT, FP8>

@@ -43,6 +43,44 @@ extern std::atomic<uint64_t> g_launches;
       return ::vltr::fail(VLTR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));    \
   } while (0)
 
+// ---- launches --------------------------------------------------------------------------------
+// Every hot-path kernel is launched with the programmatic-stream-serialization attribute
+// (programmatic dependent launch, PDL): the grid may be scheduled while the previous kernel on
+// the stream is still draining, and blocks in pdl_wait() until that kernel has completed and
+// its writes are visible.  Kernels call pdl_wait() before their first read of data a
+// predecessor may have written and pdl_trigger() right after it, so a chain of short kernels
+// (one decoder layer = rms_norm, rotary, reshape_and_cache, attention, rms_norm, silu) overlaps
+// each launch + prologue with the tail of the kernel before it.  Both instructions are no-ops
+// when the predecessor is not PDL-aware (cuBLAS GEMMs of the engine) or the attribute is off
+// (vltr_tune("pdl", 0) / VLTR_PDL=0).
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// development knobs (vltr_tune): 0 = library default
+struct Tune {
+  long long attn_warps, attn_stages, attn_ctas, attn_slots, attn_cap_tokens, attn_min_tokens;
+  long long attn_trace;      // device pointer: per-warp globaltimer stamps (tools/attn_tune.py)
+};
+extern Tune g_tune;
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -46,8 +46,17 @@ __global__ void __launch_bounds__(256)
   __shared__ float red[32];
   const int nvec = hidden_size / N;
   const int64_t row = (int64_t)blockIdx.x * hidden_size;
-  Vec16<T> x[VPT];
+  Vec16<T> x[VPT], w[VPT];
   float ss = 0.f;
+  // the norm weight is a model constant: issued first so it is in flight together with the row
+  // (and, where ptxas keeps it ahead of the wait, while the previous kernel is still draining)
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = threadIdx.x + k * blockDim.x;
+    if (v < nvec) *reinterpret_cast<uint4*>(&w[k]) = ld_nc_16(weight + (int64_t)v * N);
+  }
+  pdl_wait();
+  pdl_trigger();
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
     const int v = threadIdx.x + k * blockDim.x;
@@ -91,12 +100,11 @@ __global__ void __launch_bounds__(256)
   for (int k = 0; k < VPT; ++k) {
     const int v = threadIdx.x + k * blockDim.x;
     if (v < nvec) {
-      Vec16<T> w, o;
-      *reinterpret_cast<uint4*>(&w) = *reinterpret_cast<const uint4*>(weight + (int64_t)v * N);
+      Vec16<T> o;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         const float y = rt<T>(ST<T>::to_f(x[k].v[j]) * s);
-        o.v[j] = ST<T>::from_f(y * ST<T>::to_f(w.v[j]));
+        o.v[j] = ST<T>::from_f(y * ST<T>::to_f(w[k].v[j]));
       }
       st_16(dst + row + (int64_t)v * N, *reinterpret_cast<uint4*>(&o));
     }
@@ -148,13 +156,13 @@ int launch_rms(void* out, void* input, void* residual, const void* weight, float
     int threads = nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32;
     const int vpt = (nvec + threads - 1) / threads;
     if (vpt <= 1)
-      rms_vec_kernel<T, 1, FUSED><<<num_tokens, threads, 0, stream>>>(o, in, res, w, eps, hidden);
+      launch(rms_vec_kernel<T, 1, FUSED>, dim3(num_tokens), dim3(threads), 0, stream, o, in, res, w, eps, hidden);
     else if (vpt <= 2)
-      rms_vec_kernel<T, 2, FUSED><<<num_tokens, threads, 0, stream>>>(o, in, res, w, eps, hidden);
+      launch(rms_vec_kernel<T, 2, FUSED>, dim3(num_tokens), dim3(threads), 0, stream, o, in, res, w, eps, hidden);
     else if (vpt <= 4)
-      rms_vec_kernel<T, 4, FUSED><<<num_tokens, threads, 0, stream>>>(o, in, res, w, eps, hidden);
+      launch(rms_vec_kernel<T, 4, FUSED>, dim3(num_tokens), dim3(threads), 0, stream, o, in, res, w, eps, hidden);
     else
-      rms_vec_kernel<T, 8, FUSED><<<num_tokens, threads, 0, stream>>>(o, in, res, w, eps, hidden);
+      launch(rms_vec_kernel<T, 8, FUSED>, dim3(num_tokens), dim3(threads), 0, stream, o, in, res, w, eps, hidden);
   } else {
     int threads = hidden < 1024 ? ((hidden + 31) / 32) * 32 : 1024;
     rms_generic_kernel<T, FUSED><<<num_tokens, threads, 0, stream>>>(o, in, res, w, eps, hidden);

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256)
                          int64_t key_stride, int num_heads, int num_kv_heads, int head_size,
                          int64_t num_items) {
   constexpr int N = Vec16<T>::N;
+  pdl_wait();
+  pdl_trigger();
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= num_items) return;
   const int embed = rot_dim >> 1;
@@ -104,9 +106,9 @@ int launch_rope(const int64_t* positions, void* query, void* key, int64_t num_to
                       (uintptr_t)key % 16 == 0 && (uintptr_t)cache % 16 == 0;
   if (vec_ok) {
     const int64_t items = num_tokens * heads * (embed / N);
-    rope_neox_vec_kernel<T><<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
-        positions, (T*)query, (T*)key, (const T*)cache, offsets, rot_dim, query_stride,
-        key_stride, num_heads, num_kv_heads, head_size, items);
+    launch(rope_neox_vec_kernel<T>, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, stream,
+           positions, (T*)query, (T*)key, (const T*)cache, offsets, rot_dim, query_stride,
+           key_stride, num_heads, num_kv_heads, head_size, items);
   } else {
     const int64_t items = num_tokens * heads * embed;
     const unsigned grid = (unsigned)((items + 255) / 256);

@@ -164,6 +164,30 @@ class DecodeHotPath:
         self.scale = float(scale)
         self.attn_events = None   # optional [(start, end)] CUDA events around each attention call
 
+    def capture(self, hidden_in, positions, slot_mapping, block_tables, context_lens,
+                max_context_len: int):
+        """Record one decode step into a CUDA graph over the given (static) input tensors and
+        return ``(graph, output)``: the caller refreshes the inputs in place and calls
+        ``graph.replay()``.  ``max_context_len`` is baked into the recorded launches (it sizes the
+        attention partitions), so a graph is valid for contexts up to that bound - the engine
+        keys its graphs the same way (model_runner.py:896-970 pads to the captured batch size and
+        passes the model's max context length).  The first, uncaptured step lets the library
+        grow its workspaces; nothing allocates while recording.  Single-GPU only: the fused
+        tensor-parallel exchange takes its barrier epoch as a launch argument."""
+        if getattr(self, "comm", None) is not None:
+            raise RuntimeError("capture(): the fused tensor-parallel exchange is not graph-safe")
+        assert self.attn_events is None
+        args = (hidden_in, positions, slot_mapping, block_tables, context_lens, max_context_len)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.step(*args)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.step(*args)
+        return graph, out
+
     def attach_fused_tp(self, comm) -> None:
         """Tensor-parallel mode with the fused exchange (vllm_ltr_b200.parallel.FusedTPComm): the
         row-parallel GEMM outputs, the residual and the normed activations live in the

@@ -8,11 +8,14 @@ fused_add_rms_norm -> silu_and_mul, then the final norm (vllm_ltr_b200/hotpath.p
 GEMMs between them are library code outside this path and are NOT executed or counted).
 Contexts are the running contexts of a synthetic ShareGPT-shaped trace.
 
-  value     tokens/s with every input already resident in HBM (CUDA events, max over ranks)
+  value     tokens/s with every input already resident in HBM (CUDA events, max over ranks);
+            at N=1 the step is replayed from a CUDA graph (DecodeHotPath.capture), at N>1 it is
+            issued kernel by kernel
   e2e       the same step driven from HOST buffers: per step the engine's host-built inputs
             (positions, slot_mapping, block_tables, context_lens, token hidden rows) are copied
             from pinned memory, and the final-norm output is read back, inside the timed region
-  roofline  paged attention (the dominant kernel): algorithmic bytes per call / mean call time
+  roofline  paged attention (the dominant kernel): algorithmic bytes per call / mean call time,
+            every call bracketed by CUDA events in an eager pass of the same K steps
   cpu_baseline / --impl reference: the reference's own CPU kernels (csrc/cpu, built into
             oracle/_ref by oracle/Makefile) driven through the same call sequence on host cores.
 
@@ -263,7 +266,11 @@ class OraclePort:
             def paged_attention_v1(out, q, kc, vc, hkv, scale, bt, cl, bs, mx, alibi, kvd, kvs):
                 out.copy_(K.paged_attention(q, kc, vc, bt, cl, scale, alibi, kvd).to(out.dtype))
 
-            paged_attention_v2 = None
+            @staticmethod
+            def paged_attention_v2(out, es, ml, tmp, q, kc, vc, hkv, scale, bt, cl, bs, mx, alibi,
+                                   kvd, kvs):
+                # same result; the partition scratch is an implementation detail of the kernels
+                out.copy_(K.paged_attention(q, kc, vc, bt, cl, scale, alibi, kvd).to(out.dtype))
 
         class CacheOps:
             @staticmethod
@@ -362,9 +369,9 @@ def _main(out):
     ap.add_argument("--cpu-sample-batch", type=int, default=256)
     ap.add_argument("--tp-exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused peer-memory all-reduce+norm kernel, or NCCL all_reduce + norm")
-    ap.add_argument("--e2e-launch", default="graph", choices=["graph", "eager"],
-                    help="N=1 e2e leg: replay the step from a CUDA graph (default) or issue it "
-                         "kernel by kernel")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="N=1: replay the step from a CUDA graph (default) or issue it kernel by "
+                         "kernel (N>1 is always kernel by kernel)")
     ap.add_argument("--no-pdl", action="store_true",
                     help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-tick", dest="tick", action="store_false",
@@ -465,15 +472,25 @@ def _main(out):
             tick()
         return out
 
-    # e2e leg at N=1: the step is recorded once into a CUDA graph over static device inputs; per
-    # step the host buffers are copied into them, the graph is replayed and the result read back
-    use_graph = world == 1 and args.e2e_launch == "graph"
+    # N=1: the step is recorded once into a CUDA graph over static device inputs (the launch
+    # mode a latency-sensitive caller uses; PDL edges between the kernels are kept by the graph).
+    # `value` replays it with the inputs resident; the e2e leg copies the host buffers into the
+    # static inputs, replays, and reads the result back.  N>1 issues kernel by kernel (the fused
+    # exchange takes its barrier epoch as a launch argument).
+    use_graph = world == 1 and args.launch == "graph"
     graph = graph_out = None
+    launches_per_graph = 0
     if use_graph:
         n_before = launch_count()
         graph, graph_out = hp.capture(devin["hidden"], devin["positions"], devin["slot_mapping"],
                                       devin["block_tables"], devin["context_lens"], max_ctx)
         launches_per_graph = (launch_count() - n_before) // 2     # warm-up step + recorded step
+
+    def step_graph():
+        graph.replay()
+        if tick:
+            tick()
+        return graph_out
 
     def step_e2e():
         if use_graph:
@@ -502,7 +519,8 @@ def _main(out):
         step_resident()
     barrier()
 
-    # timed region 1: inputs resident, device time
+    # timed region 1 (eager, inputs resident): every paged_attention call is bracketed by CUDA
+    # events on its stream -> the roofline numbers; at N>1 this region is also `value`
     hp.attn_events = []
     n0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -512,11 +530,26 @@ def _main(out):
         step_resident()
     e1.record()
     barrier()
-    t_end = time.time()
     launches = launch_count() - n0
-    ms = e0.elapsed_time(e1)
+    ms_eager = ms = e0.elapsed_time(e1)
     attn_ms = [a.elapsed_time(b) for a, b in hp.attn_events]
     hp.attn_events = None
+
+    # timed region 1g (N=1, inputs resident): the same K steps replayed from the CUDA graph
+    if use_graph:
+        for _ in range(2):
+            step_graph()
+        barrier()
+        n0 = launch_count()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            step_graph()
+        g1.record()
+        barrier()
+        launches = launch_count() - n0 + launches_per_graph * args.steps
+        ms = g0.elapsed_time(g1)
+    t_end = time.time()
 
     # host cost of issuing the decode ops of one step (no device wait, tick excluded): must
     # stay below the device time or the step becomes launch-bound
@@ -577,7 +610,10 @@ def _main(out):
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
                 "launch_ms_mean": attn_mean_ms, "launches_timed": len(attn_ms),
-                "attention_share_of_step": float(np.sum(attn_ms)) / ms if attn_ms else None,
+                "timed_in": "eager pass of the same K steps (events cannot bracket kernels inside "
+                            "a graph replay)" if use_graph else "the timed region",
+                "attention_share_of_step": float(np.sum(attn_ms)) / ms_eager if attn_ms else None,
+                "eager_ms_per_step": ms_eager / args.steps,
                 "step_achieved_gbs": step_bytes(ctx, shape, bs, shape.layers) / (ms_per_step * 1e-3) / 1e9}
 
     line = {
@@ -589,6 +625,7 @@ def _main(out):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                 "launch": ("cuda graph replay (%d kernels per step)" % launches_per_graph
                            if use_graph else "eager")},
+        "launch": "cuda graph replay" if use_graph else "eager",
         "pdl": not args.no_pdl,
         "gpu_launches": int(launches), "roofline": roofline,
         "host_issue_ms_per_step": host_ms, "tick_ms_alone": tick_ms,

@@ -47,7 +47,7 @@ const char* vltr_build_info(void);
 uint64_t vltr_launch_count(void);
 /* development knobs, not part of the reference surface.  "pdl" 0/1: launch the hot-path kernels
  * with programmatic dependent launch (default 1, env VLTR_PDL); "attn_warps", "attn_stages",
- * "attn_ctas", "attn_slots", "attn_cap_tokens", "attn_min_tokens": override the paged-attention
+ * "attn_ctas", "attn_slots", "attn_cap_tokens", "attn_min_tokens", "attn_l2_ahead": override the paged-attention
  * launch policy (0 = default); "attn_trace": device pointer receiving per-warp timestamps. */
 int vltr_tune(const char* key, long long value);
 
@@ -242,6 +242,23 @@ int vltr_tp_allreduce(const vltr_tp_comm* comm, int num_tokens, int hidden_size,
                       void* stream);
 int vltr_tp_allreduce_add_rms_norm(const vltr_tp_comm* comm, const void* weight, float epsilon,
                                    int num_tokens, int hidden_size, int dtype, void* stream);
+
+/* ---- sampler (next row after the decode path) ------------------------------
+ * Replaces the tensor program of Sampler.forward for greedy / temperature-only random sampling
+ * (vllm/model_executor/layers/sampler.py:67 temperature, :77-80 softmax + log_softmax in fp32,
+ * :395 greedy argmax, :333-357 _multinomial = argmax(probs / Exp(1) noise), :528-544 _get_ranks,
+ * :594-600 logprob of the chosen token) with one pass over the logits.
+ * logits [num_rows, vocab] (dtype f32/f16/bf16, row stride in elements); temperatures [num_rows]
+ * float (already rounded to the logits dtype, as the reference's temperature tensor is) or NULL
+ * (= 1.0); random [num_rows] bytes, 0 = greedy, 1 = random, NULL = all greedy; noise [num_rows,
+ * vocab] float Exp(1) samples, or NULL to draw them in the kernel (Philox4x32-10 keyed by seed,
+ * counter = (column/4, row, offset)).  Outputs: out_token [num_rows] int64 (required),
+ * out_logprob [num_rows] float, out_rank [num_rows] int64, and the full fp32 matrices out_probs /
+ * out_logprobs [num_rows, vocab] for callers that need top-k logprobs - each may be NULL. */
+int vltr_sample(const void* logits, int64_t row_stride, int num_rows, int vocab, int dtype,
+                const float* temperatures, const uint8_t* random, const float* noise,
+                uint64_t seed, uint64_t offset, int64_t* out_token, float* out_logprob,
+                int64_t* out_rank, float* out_probs, float* out_logprobs, void* stream);
 
 /* ---- cuda utils: csrc/cuda_utils_kernels.cu ---------------------------------------------- */
 int vltr_get_device_attribute(int attribute, int device_id);

@@ -114,9 +114,14 @@ def main():
                  {"attn_slots": 32}, {"attn_cap_tokens": 256}, {"attn_cap_tokens": 128},
                  {"attn_cap_tokens": 256, "attn_slots": 16}, {"attn_ctas": 3, "attn_slots": 12},
                  {"attn_ctas": 4, "attn_slots": 16}, {"attn_ctas": 4, "attn_slots": 16, "attn_cap_tokens": 256}],
+        "r2": [{}, {"attn_ctas": 2}, {"attn_ctas": 3}, {"attn_ctas": 4}, {"attn_ctas": 1},
+               {"attn_l2_ahead": 2}, {"attn_l2_ahead": 4}, {"attn_l2_ahead": 8}, {"attn_l2_ahead": 16},
+               {"attn_slots": 12}, {"attn_slots": 16}, {"attn_slots": 24},
+               {"attn_slots": 16, "attn_l2_ahead": 4}, {"attn_slots": 16, "attn_l2_ahead": 8},
+               {"attn_ctas": 2, "attn_l2_ahead": 8}, {"attn_ctas": 4, "attn_l2_ahead": 8}],
     }[args.grid]
     keys = ("pdl", "attn_ctas", "attn_warps", "attn_stages", "attn_slots", "attn_cap_tokens",
-            "attn_min_tokens")
+            "attn_min_tokens", "attn_l2_ahead")
     rows = []
     for spec in args.cases.split(","):
         name, B, mode = spec.split(":")
@@ -143,7 +148,7 @@ def main():
         for k in keys:
             tune(k, 1 if k == "pdl" else 0)
         if args.trace:
-            nw = 148 * 8 * 2
+            nw = 148 * 16 * 2
             buf = torch.zeros(nw * 8, dtype=torch.int64, device=DEV)
             for i in range(3):
                 launch(_C.ops, c, i)
@@ -167,6 +172,13 @@ def main():
             if worked.any():
                 print(f"     first KV tile landed  {pct(first[worked])}")
             print(f"     warp finished         {pct(end)}")
+            w = worked & (t[:, 7] > 0)
+            if w.any():
+                frac = t[w, 6] / t[w, 7]
+                cyc = (t[w, 7] - t[w, 6]) / t[w, 5]
+                print(f"     tile loop: waiting for KV {np.median(frac)*100:.0f}% of the time (p10 "
+                      f"{np.percentile(frac,10)*100:.0f}%, p90 {np.percentile(frac,90)*100:.0f}%); "
+                      f"compute {np.median(cyc):.0f} SM cycles per tile")
             print(f"     items per warp  min {t[:,4].min()} p50 {np.median(t[:,4]):.0f} max {t[:,4].max()};"
                   f"  KV tiles per warp  min {t[:,5].min()} p50 {np.median(t[:,5]):.0f} max {t[:,5].max()}",
                   flush=True)

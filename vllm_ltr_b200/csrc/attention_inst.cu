@@ -23,8 +23,10 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    // target two 4-warp CTAs per SM; shrink warps/CTA when tiles are too large for that
-    const int ctas = want_ctas > 0 ? want_ctas : 2;
+    // Resident warps per SM matter more than ring depth (measured, tools/attn_tune.py): three
+    // 4-warp CTAs with a 2-deep ring beat two with a 3-deep ring by 5-7% on 2-byte caches, and
+    // the e5m2 path (more instructions per byte: byte-permute conversions) wants four.
+    const int ctas = want_ctas > 0 ? want_ctas : (C::FP8 ? 4 : 3);
     int budget = sm_smem / ctas - 1024 - kPlanBytes;       // 1 KiB per CTA is reserved by the system
     if (budget > max_optin - kPlanBytes) budget = max_optin - kPlanBytes;
     int warps = want_warps > 0 ? want_warps : 4, stages = 0;
@@ -74,6 +76,7 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
   if (grid > need) grid = (int)need;
   if (grid < 1) grid = 1;
   p.trace = reinterpret_cast<long long*>(g_tune.attn_trace);
+  p.l2_ahead = (int)g_tune.attn_l2_ahead;
   launch(kern, dim3(grid), dim3(plan.warps * 32), (size_t)plan.smem, stream, p);
   VLTR_LAUNCH_CHECK("paged_attention");
   return VLTR_OK;

@@ -70,6 +70,7 @@ struct Params {
   int64_t kv_block_stride;      // bytes
   int64_t kv_head_stride;       // bytes
   int stages;
+  int l2_ahead;                 // KV tiles requested into L2 beyond the shared-memory ring (0 = off)
   int use_plan;                 // 1: items enumerate only non-empty partitions (num_seqs <= kMaxPlanSeqs)
   int* counters;                // [0] next item, [1] finished warps   (self-resetting)
   int* tickets;                 // [num_seqs * passes * num_kv_heads] partition tickets, all zero
@@ -113,6 +114,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
           "r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+// fire-and-forget request to bring a span into L2 (no shared memory, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   uint4 r;
@@ -434,6 +439,7 @@ struct Item {
   int ctx, nparts;      // context length and number of partitions of this sequence
   int blk0, ntiles;     // first KV block and number of KV blocks of this partition
   int issued;           // tiles handed to the TMA ring so far
+  int pref;             // tiles requested into L2 ahead of the ring so far
   int bt0, bt1;         // lane i holds the block ids of tiles i and 32+i
 };
 
@@ -457,6 +463,7 @@ __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p,
   const int item = __shfl_sync(0xffffffffu, pending_id, 0);
   it.valid = item < total_items;
   it.issued = 0;
+  it.pref = 0;
   it.ntiles = 0;
   if (!it.valid) return;
   it.kvh = item % p.num_kv_heads;
@@ -519,6 +526,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   long long* tr = p.trace != nullptr ? p.trace + ((int64_t)blockIdx.x * nwarps + warp) * 8 : nullptr;
   if (tr != nullptr && lane == 0) tr[0] = gtime();
   int tr_items = 0, tr_tiles = 0;
+  long long tr_wait = 0, tr_loop0 = 0, tr_loop = 0;
   const int wbytes = warp_smem_bytes<C>(S);
   unsigned char* wbase = smem_raw + (size_t)warp * wbytes;
   const uint32_t tiles_s = smem_u32(wbase);                        // S x {K tile, V tile}
@@ -671,6 +679,22 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       ++it.issued;
       ++inflight;
     }
+    // The ring is as deep as shared memory allows (S tiles per warp); when few warps have work
+    // (tails, small batches) that depth, not HBM, bounds a warp's rate.  Tiles beyond the ring are
+    // therefore requested into L2 early, so the later shared-memory fill is an L2 hit.
+    if (p.l2_ahead > 0) {
+      const int want = min(it.issued + p.l2_ahead, it.ntiles);
+      if (it.pref < it.issued) it.pref = it.issued;
+      while (it.pref < want) {
+        const int i = it.pref;
+        const int bid = __shfl_sync(0xffffffffu, i < 32 ? it.bt0 : it.bt1, i & 31);
+        if (lane == 0) {
+          bulk_prefetch_l2(kbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES);
+          bulk_prefetch_l2(vbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES);
+        }
+        ++it.pref;
+      }
+    }
   };
 
   // Work-item lookahead.  The queue ticket for the NEXT item is drawn (async atomic) when the
@@ -783,6 +807,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       __syncwarp();
     }
 
+    if (tr != nullptr) tr_loop0 = clock64();
     for (int tile = 0; tile < ntiles; ++tile) {
       if (!pend_valid && !nxt_ready && ntiles - tile <= S + 2) {
         pend = fetch_id(p, lane);
@@ -795,8 +820,11 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       }
       const uint32_t ktile = tiles_s + stage_c * 2 * C::TILE_BYTES;
       const uint32_t vtile = ktile + C::TILE_BYTES;
+      long long tw0 = 0;
+      if (tr != nullptr) tw0 = clock64();
       mbar_wait(bars + 8 * stage_c, phase_c);
       if (tr != nullptr) {
+        tr_wait += clock64() - tw0;
         if (tr_tiles == 0 && lane == 0) tr[2] = gtime();
         ++tr_tiles;
       }
@@ -1012,6 +1040,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       if (nxt_ready) pump(nxt);
     }
 
+    if (tr != nullptr) tr_loop += clock64() - tr_loop0;
     // ---- epilogue: finish the reductions, normalise, store / publish the partial ----------------
     // Layout-independent description of what this lane owns: FMA: head h, rows v_row + i*RPI
     // (lanes v_sub == 0); MMA: rows g (+8), columns 8nd + 2t4 + {0,1}.
@@ -1109,6 +1138,8 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     tr[3] = gtime();
     tr[4] = tr_items;
     tr[5] = tr_tiles;
+    tr[6] = tr_wait;      // SM cycles spent waiting for tiles
+    tr[7] = tr_loop;      // SM cycles in the tile loops (waiting + computing)
   }
 
   // self-resetting queue: the last warp to leave zeroes the counters for the next launch

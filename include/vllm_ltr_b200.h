@@ -47,7 +47,7 @@ const char* vltr_build_info(void);
 uint64_t vltr_launch_count(void);
 /* development knobs, not part of the reference surface.  "pdl" 0/1: launch the hot-path kernels
  * with programmatic dependent launch (default 1, env VLTR_PDL); "attn_warps", "attn_stages",
- * "attn_ctas", "attn_slots", "attn_cap_tokens", "attn_min_tokens", "attn_l2_ahead": override the paged-attention
+ * "attn_ctas", "attn_slots", "attn_cap_tokens", "attn_min_tokens": override the paged-attention
  * launch policy (0 = default); "attn_trace": device pointer receiving per-warp timestamps. */
 int vltr_tune(const char* key, long long value);
 

@@ -114,14 +114,11 @@ def main():
                  {"attn_slots": 32}, {"attn_cap_tokens": 256}, {"attn_cap_tokens": 128},
                  {"attn_cap_tokens": 256, "attn_slots": 16}, {"attn_ctas": 3, "attn_slots": 12},
                  {"attn_ctas": 4, "attn_slots": 16}, {"attn_ctas": 4, "attn_slots": 16, "attn_cap_tokens": 256}],
-        "r2": [{}, {"attn_ctas": 2}, {"attn_ctas": 3}, {"attn_ctas": 4}, {"attn_ctas": 1},
-               {"attn_l2_ahead": 2}, {"attn_l2_ahead": 4}, {"attn_l2_ahead": 8}, {"attn_l2_ahead": 16},
-               {"attn_slots": 12}, {"attn_slots": 16}, {"attn_slots": 24},
-               {"attn_slots": 16, "attn_l2_ahead": 4}, {"attn_slots": 16, "attn_l2_ahead": 8},
-               {"attn_ctas": 2, "attn_l2_ahead": 8}, {"attn_ctas": 4, "attn_l2_ahead": 8}],
+        "r3": [{}, {"attn_slots": 12}, {"attn_slots": 16}, {"attn_cap_tokens": 256},
+               {"attn_min_tokens": 128}, {"attn_min_tokens": 256}],
     }[args.grid]
     keys = ("pdl", "attn_ctas", "attn_warps", "attn_stages", "attn_slots", "attn_cap_tokens",
-            "attn_min_tokens", "attn_l2_ahead")
+            "attn_min_tokens")
     rows = []
     for spec in args.cases.split(","):
         name, B, mode = spec.split(":")
@@ -149,7 +146,7 @@ def main():
             tune(k, 1 if k == "pdl" else 0)
         if args.trace:
             nw = 148 * 16 * 2
-            buf = torch.zeros(nw * 8, dtype=torch.int64, device=DEV)
+            buf = torch.zeros(nw * 16, dtype=torch.int64, device=DEV)
             for i in range(3):
                 launch(_C.ops, c, i)
             torch.cuda.synchronize()
@@ -158,7 +155,7 @@ def main():
                 launch(_C.ops, c, i)
             torch.cuda.synchronize()
             tune("attn_trace", 0)
-            t = buf.cpu().numpy().reshape(nw, 8)
+            t = buf.cpu().numpy().reshape(nw, 16)
             t = t[t[:, 0] != 0]
             t0 = t[:, 0].min()
             start, plan, first, end = (t[:, i] - t0 for i in range(4))
@@ -179,6 +176,16 @@ def main():
                 print(f"     tile loop: waiting for KV {np.median(frac)*100:.0f}% of the time (p10 "
                       f"{np.percentile(frac,10)*100:.0f}%, p90 {np.percentile(frac,90)*100:.0f}%); "
                       f"compute {np.median(cyc):.0f} SM cycles per tile")
+            if worked.any():
+                tw = t[worked]
+                for label, sel in (("single-partition", tw[:, 12] == 1), ("multi-partition", tw[:, 12] > 1)):
+                    if sel.any():
+                        x = tw[sel]
+                        print(f"     last item of a warp, {label} ({int(sel.sum())} warps, {np.median(x[:,13]):.0f} tiles p50): "
+                              f"tiles {np.median(x[:,9]-x[:,8])/1e3:.1f} us (max {np.max(x[:,9]-x[:,8])/1e3:.1f}), "
+                              f"store {np.median(x[:,10]-x[:,9])/1e3:.1f} us, "
+                              f"ticket+merge {np.median(x[:,11]-x[:,10])/1e3:.1f} us (max {np.max(x[:,11]-x[:,10])/1e3:.1f}), "
+                              f"exit after {np.median(x[:,3]-x[:,11])/1e3:.1f} us")
             print(f"     items per warp  min {t[:,4].min()} p50 {np.median(t[:,4]):.0f} max {t[:,4].max()};"
                   f"  KV tiles per warp  min {t[:,5].min()} p50 {np.median(t[:,5]):.0f} max {t[:,5].max()}",
                   flush=True)

@@ -25,7 +25,10 @@ for s in $STEPS; do
     prefilltests) timeout 900 python -m pytest tests/test_gpu_prefill.py tests/test_gpu_properties.py -q --maxfail=20 -p no:cacheprovider > $OUT/prefilltests.log 2>&1; echo "prefilltests rc=$?"; tail -25 $OUT/prefilltests.log ;;
     hotpathtests) timeout 600 python -m pytest tests/test_gpu_hotpath.py -q -p no:cacheprovider > $OUT/hotpathtests.log 2>&1; echo "hotpathtests rc=$?"; tail -15 $OUT/hotpathtests.log ;;
     tune)    timeout 900 python tools/attn_tune.py --grid wide --trace --ref --json $OUT/attn_tune.json > $OUT/attn_tune.log 2>&1; echo "tune rc=$?"; cat $OUT/attn_tune.log ;;
-    tune2)   timeout 900 python tools/attn_tune.py --grid r2 --trace --json $OUT/attn_tune2.json > $OUT/attn_tune2.log 2>&1; echo "tune2 rc=$?"; cat $OUT/attn_tune2.log ;;
+    chain)   timeout 600 python tools/chain_bench.py --json $OUT/chain.json > $OUT/chain.log 2>&1; echo "chain rc=$?"; cat $OUT/chain.log ;;
+    tune3)   timeout 900 python tools/attn_tune.py --grid r3 --trace --cases 70b-tp8-bf16:256:trace,8b-gqa-bf16:64:trace,8b-gqa-bf16:256:trace,7b-mha-bf16:64:trace --json $OUT/attn_tune3.json > $OUT/attn_tune3.log 2>&1; echo "tune3 rc=$?"; cat $OUT/attn_tune3.log ;;
+    samplertests) timeout 600 python -m pytest tests/test_gpu_sampler.py -q -p no:cacheprovider > $OUT/samplertests.log 2>&1; echo "samplertests rc=$?"; tail -25 $OUT/samplertests.log ;;
+    tune2)   timeout 900 python tools/attn_tune.py --grid r3 --trace --json $OUT/attn_tune2.json > $OUT/attn_tune2.log 2>&1; echo "tune2 rc=$?"; cat $OUT/attn_tune2.log ;;
     tuneq)   timeout 600 python tools/attn_tune.py --trace --json $OUT/attn_tuneq.json > $OUT/attn_tuneq.log 2>&1; echo "tuneq rc=$?"; cat $OUT/attn_tuneq.log ;;
     benchab) timeout 600 python bench.py --no-pdl --launch eager --no-cpu-baseline > $OUT/bench_nopdl_eager.json 2> $OUT/bench_ab.err; echo "benchab rc=$?"; cat $OUT/bench_nopdl_eager.json ;;
     benchmodels) for m in llama-3-8b llama-3-8b-fp8kv; do timeout 600 python bench.py --model $m --no-cpu-baseline > $OUT/bench_$m.json 2> $OUT/bench_$m.err; echo "bench $m rc=$?"; cat $OUT/bench_$m.json; done ;;

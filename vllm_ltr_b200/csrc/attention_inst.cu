@@ -76,7 +76,6 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
   if (grid > need) grid = (int)need;
   if (grid < 1) grid = 1;
   p.trace = reinterpret_cast<long long*>(g_tune.attn_trace);
-  p.l2_ahead = (int)g_tune.attn_l2_ahead;
   launch(kern, dim3(grid), dim3(plan.warps * 32), (size_t)plan.smem, stream, p);
   VLTR_LAUNCH_CHECK("paged_attention");
   return VLTR_OK;

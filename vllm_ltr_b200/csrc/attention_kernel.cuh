@@ -70,11 +70,10 @@ struct Params {
   int64_t kv_block_stride;      // bytes
   int64_t kv_head_stride;       // bytes
   int stages;
-  int l2_ahead;                 // KV tiles requested into L2 beyond the shared-memory ring (0 = off)
   int use_plan;                 // 1: items enumerate only non-empty partitions (num_seqs <= kMaxPlanSeqs)
   int* counters;                // [0] next item, [1] finished warps   (self-resetting)
   int* tickets;                 // [num_seqs * passes * num_kv_heads] partition tickets, all zero
-  long long* trace;             // development: 8 stamps per warp (tools/attn_tune.py) or null
+  long long* trace;             // development: 16 stamps per warp (tools/attn_tune.py) or null
 };
 __device__ __forceinline__ long long gtime() {
   long long t;
@@ -114,10 +113,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
           "r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
-}
-// fire-and-forget request to bring a span into L2 (no shared memory, no completion tracking)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   uint4 r;
@@ -439,7 +434,6 @@ struct Item {
   int ctx, nparts;      // context length and number of partitions of this sequence
   int blk0, ntiles;     // first KV block and number of KV blocks of this partition
   int issued;           // tiles handed to the TMA ring so far
-  int pref;             // tiles requested into L2 ahead of the ring so far
   int bt0, bt1;         // lane i holds the block ids of tiles i and 32+i
 };
 
@@ -463,7 +457,6 @@ __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p,
   const int item = __shfl_sync(0xffffffffu, pending_id, 0);
   it.valid = item < total_items;
   it.issued = 0;
-  it.pref = 0;
   it.ntiles = 0;
   if (!it.valid) return;
   it.kvh = item % p.num_kv_heads;
@@ -523,7 +516,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int S = p.stages;
-  long long* tr = p.trace != nullptr ? p.trace + ((int64_t)blockIdx.x * nwarps + warp) * 8 : nullptr;
+  long long* tr = p.trace != nullptr ? p.trace + ((int64_t)blockIdx.x * nwarps + warp) * 16 : nullptr;
   if (tr != nullptr && lane == 0) tr[0] = gtime();
   int tr_items = 0, tr_tiles = 0;
   long long tr_wait = 0, tr_loop0 = 0, tr_loop = 0;
@@ -679,22 +672,6 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       ++it.issued;
       ++inflight;
     }
-    // The ring is as deep as shared memory allows (S tiles per warp); when few warps have work
-    // (tails, small batches) that depth, not HBM, bounds a warp's rate.  Tiles beyond the ring are
-    // therefore requested into L2 early, so the later shared-memory fill is an L2 hit.
-    if (p.l2_ahead > 0) {
-      const int want = min(it.issued + p.l2_ahead, it.ntiles);
-      if (it.pref < it.issued) it.pref = it.issued;
-      while (it.pref < want) {
-        const int i = it.pref;
-        const int bid = __shfl_sync(0xffffffffu, i < 32 ? it.bt0 : it.bt1, i & 31);
-        if (lane == 0) {
-          bulk_prefetch_l2(kbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES);
-          bulk_prefetch_l2(vbase + (int64_t)bid * p.kv_block_stride, C::TILE_BYTES);
-        }
-        ++it.pref;
-      }
-    }
   };
 
   // Work-item lookahead.  The queue ticket for the NEXT item is drawn (async atomic) when the
@@ -807,7 +784,10 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       __syncwarp();
     }
 
-    if (tr != nullptr) tr_loop0 = clock64();
+    if (tr != nullptr) {
+      tr_loop0 = clock64();
+      if (lane == 0) tr[8] = gtime();       // item set up (claimed, q staged)
+    }
     for (int tile = 0; tile < ntiles; ++tile) {
       if (!pend_valid && !nxt_ready && ntiles - tile <= S + 2) {
         pend = fetch_id(p, lane);
@@ -881,30 +861,49 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         uint32_t pa[C::KT][4];
 #pragma unroll
         for (int kt = 0; kt < C::KT; ++kt) pa[kt][0] = pa[kt][1] = pa[kt][2] = pa[kt][3] = 0u;
+        // only the context's last block can hold out-of-context tokens, and ALiBi is rare: the
+        // common tile takes the short form (bit-identical: slope == 0 adds +0)
+        const bool plain = !last_partial && p.alibi_slopes == nullptr;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           float mx = -INFINITY;
+          if (plain) {
 #pragma unroll
-          for (int nt = 0; nt < C::NT; ++nt) {
+            for (int nt = 0; nt < C::NT; ++nt) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int tok = tok0 + 8 * nt + 2 * t4 + e;
-              float sv = s[nt][2 * r + e] * scale_l2 + slope[r] * (float)(tok - ctx + 1);
-              sv = tok < ctx ? sv : -INFINITY;
-              s[nt][2 * r + e] = sv;
-              mx = fmaxf(mx, sv);
+              for (int e = 0; e < 2; ++e) {
+                const float sv = s[nt][2 * r + e] * scale_l2;
+                s[nt][2 * r + e] = sv;
+                mx = fmaxf(mx, sv);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int nt = 0; nt < C::NT; ++nt) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int tok = tok0 + 8 * nt + 2 * t4 + e;
+                float sv = s[nt][2 * r + e] * scale_l2 + slope[r] * (float)(tok - ctx + 1);
+                sv = tok < ctx ? sv : -INFINITY;
+                s[nt][2 * r + e] = sv;
+                mx = fmaxf(mx, sv);
+              }
             }
           }
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
           const float m_new = fmaxf(m[r], mx);    // finite: a scheduled tile has a valid token
-          const float alpha = exp2f(m[r] - m_new);
-          m[r] = m_new;
-          l[r] *= alpha;
+          // the running maximum settles after the first tiles: rescale only when some row's
+          // maximum moved (warp-uniform; alpha == 1 exactly otherwise)
+          if (__any_sync(0xffffffffu, m_new != m[r])) {
+            const float alpha = exp2f(m[r] - m_new);
+            m[r] = m_new;
+            l[r] *= alpha;
 #pragma unroll
-          for (int i = 0; i < C::ND; ++i) {
-            o_acc[i][2 * r] *= alpha;
-            o_acc[i][2 * r + 1] *= alpha;
+            for (int i = 0; i < C::ND; ++i) {
+              o_acc[i][2 * r] *= alpha;
+              o_acc[i][2 * r + 1] *= alpha;
+            }
           }
 #pragma unroll
           for (int nt = 0; nt < C::NT; ++nt) {
@@ -1040,7 +1039,10 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       if (nxt_ready) pump(nxt);
     }
 
-    if (tr != nullptr) tr_loop += clock64() - tr_loop0;
+    if (tr != nullptr) {
+      tr_loop += clock64() - tr_loop0;
+      if (lane == 0) tr[9] = gtime();       // tiles done
+    }
     // ---- epilogue: finish the reductions, normalise, store / publish the partial ----------------
     // Layout-independent description of what this lane owns: FMA: head h, rows v_row + i*RPI
     // (lanes v_sub == 0); MMA: rows g (+8), columns 8nd + 2t4 + {0,1}.
@@ -1113,6 +1115,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       }
     }
 
+    if (tr != nullptr && lane == 0) tr[10] = gtime();   // result / partial stored
     // ---- merge: the warp that publishes a sequence's LAST partition combines them all ------------
     // (reference: paged_attention_v2_reduce_kernel, :511-602: weights exp_sum_j*exp(max_j-max) /
     // (sum + 1e-6) over per-partition normalised outputs)
@@ -1131,6 +1134,11 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     }
     __syncwarp();  // q_s / p_s are rewritten by the next item
     ++tr_items;
+    if (tr != nullptr && lane == 0) {
+      tr[11] = gtime();                     // merge (if any) done
+      tr[12] = cur.nparts;
+      tr[13] = ntiles;
+    }
 
     advance();
   }

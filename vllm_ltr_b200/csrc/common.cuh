@@ -77,7 +77,6 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
 // development knobs (vltr_tune): 0 = library default
 struct Tune {
   long long attn_warps, attn_stages, attn_ctas, attn_slots, attn_cap_tokens, attn_min_tokens;
-  long long attn_l2_ahead;   // KV tiles prefetched into L2 beyond the shared-memory ring
   long long attn_trace;      // device pointer: per-warp globaltimer stamps (tools/attn_tune.py)
 };
 extern Tune g_tune;

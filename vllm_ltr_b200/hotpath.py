@@ -188,6 +188,19 @@ class DecodeHotPath:
             out = self.step(*args)
         return graph, out
 
+    def attention_only(self, block_tables, context_lens, max_context_len: int, T: int) -> None:
+        """The paged-attention calls of one step and nothing else: one launch per layer, each
+        over that layer's own KV pool, back to back on the current stream (bench.py times this
+        between one pair of events to get the kernel's in-stream launch duration)."""
+        s = self.shape
+        qsz = s.q_heads * s.head_size
+        q = self.qkv[:T, :qsz].view(T, s.q_heads, s.head_size)
+        out = self.attn_out[:T].view(T, s.q_heads, s.head_size)
+        for layer in range(self.layers):
+            forward_decode(q, self.key_caches[layer], self.value_caches[layer], block_tables,
+                           context_lens, max_context_len, s.kv_cache_dtype, s.kv_heads, self.scale,
+                           None, 1.0, out=out, C=self.C)
+
     def attach_fused_tp(self, comm) -> None:
         """Tensor-parallel mode with the fused exchange (vllm_ltr_b200.parallel.FusedTPComm): the
         row-parallel GEMM outputs, the residual and the normed activations live in the

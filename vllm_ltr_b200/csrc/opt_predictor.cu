@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(kGemmThreads)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot_ptr;
+  // barriers and the TMEM allocation above touch no global memory: under programmatic dependent
+  // launch they overlap the tail of the previous kernel of the forward pass
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     // ---- TMA producer ---------------------------------------------------------------------------
@@ -253,6 +257,8 @@ __global__ void __launch_bounds__(128)
     embed_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ positions,
                  const T* __restrict__ tok, const T* __restrict__ pos, T* __restrict__ out, int E,
                  int add_pos) {
+  pdl_wait();
+  pdl_trigger();
   const int t = blockIdx.x;
   const T* src = tok + (int64_t)ids[t] * E;
   const T* p = pos + ((int64_t)positions[t] + 2) * E;   // OPTLearnedPositionalEmbedding offset 2
@@ -274,6 +280,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
     add_pos_kernel(const int32_t* __restrict__ positions, const T* __restrict__ pos,
                    T* __restrict__ h, int H) {
+  pdl_wait();
+  pdl_trigger();
   const int t = blockIdx.x;
   const T* p = pos + ((int64_t)positions[t] + 2) * H;
   for (int i = threadIdx.x; i < H; i += blockDim.x)
@@ -287,6 +295,8 @@ __global__ void __launch_bounds__(128)
     layernorm_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ w,
                      const T* __restrict__ b, const int32_t* __restrict__ rows, int nrows, int H,
                      float eps, int identity) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= nrows) return;
@@ -336,6 +346,8 @@ __global__ void __launch_bounds__(kAttnRows)
                      const int32_t* __restrict__ cu_seqlens, int H, float scale) {
   __shared__ __align__(16) T sk[kAttnKeys][kHD];
   __shared__ __align__(16) T sv[kAttnKeys][kHD];
+  pdl_wait();
+  pdl_trigger();
   const int prompt = blockIdx.z, head = blockIdx.y;
   const int t0 = cu_seqlens[prompt], len = cu_seqlens[prompt + 1] - t0;
   const int q0 = blockIdx.x * kAttnRows;
@@ -423,6 +435,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
     score_kernel(const T* __restrict__ x, const T* __restrict__ w, float* __restrict__ logits,
                  int n, int labels, int E) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (idx >= n * labels) return;
@@ -483,8 +497,8 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
     configured = true;
   }
   dim3 grid(N / BN, (M + kBM - 1) / kBM);
-  kern<<<grid, kGemmThreads, gemm_smem_bytes<BN>(), stream>>>(ma, mb, (T*)D, (const T*)bias,
-                                                            (const T*)resid, M, N, K);
+  launch(kern, grid, dim3(kGemmThreads), (size_t)gemm_smem_bytes<BN>(), stream, ma, mb, (T*)D,
+         (const T*)bias, (const T*)resid, M, N, K);
   VLTR_LAUNCH_CHECK("opt_gemm");
   return VLTR_OK;
 }
@@ -548,15 +562,15 @@ static int forward_t(const Model& mdl, const int32_t* ids, const int32_t* positi
   const float scale = 1.0f / sqrtf((float)(H / c.heads));
 
   if (E == H) {
-    embed_kernel<T><<<M, 128, 0, s>>>(ids, positions, (const T*)w.embed_tokens,
+    launch(embed_kernel<T>, dim3(M), dim3(128), 0, s, ids, positions, (const T*)w.embed_tokens,
                                       (const T*)w.embed_positions, h, E, 1);
     VLTR_LAUNCH_CHECK("opt_embed");
   } else {
-    embed_kernel<T><<<M, 128, 0, s>>>(ids, positions, (const T*)w.embed_tokens,
+    launch(embed_kernel<T>, dim3(M), dim3(128), 0, s, ids, positions, (const T*)w.embed_tokens,
                                       (const T*)w.embed_positions, emb, E, 0);
     VLTR_LAUNCH_CHECK("opt_embed");
     if ((rc = gemm(emb, w.project_in, h, nullptr, nullptr, M, H, E, 0, dt, s))) return rc;
-    add_pos_kernel<T><<<M, 128, 0, s>>>(positions, (const T*)w.embed_positions, h, H);
+    launch(add_pos_kernel<T>, dim3(M), dim3(128), 0, s, positions, (const T*)w.embed_positions, h, H);
     VLTR_LAUNCH_CHECK("opt_add_pos");
   }
   const int ln_grid = (M + 3) / 4;
@@ -564,18 +578,18 @@ static int forward_t(const Model& mdl, const int32_t* ids, const int32_t* positi
   for (int L = 0; L < c.layers; ++L) {
     const T* a_in = h;
     if (c.do_layer_norm_before) {
-      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(h, x, (const T*)w.ln1_w[L], (const T*)w.ln1_b[L],
+      launch(layernorm_kernel<T>, dim3(ln_grid), dim3(128), 0, s, h, x, (const T*)w.ln1_w[L], (const T*)w.ln1_b[L],
                                                   nullptr, M, H, 1e-5f, 0);
       VLTR_LAUNCH_CHECK("opt_layernorm");
       a_in = x;
     }
     if ((rc = gemm(a_in, w.qkv_w[L], qkv, w.qkv_b[L], nullptr, M, 3 * H, H, 0, dt, s))) return rc;
-    attention_kernel<T><<<agrid, kAttnRows, 0, s>>>(qkv, att, cu_seqlens, H, scale);
+    launch(attention_kernel<T>, dim3(agrid), dim3(kAttnRows), 0, s, qkv, att, cu_seqlens, H, scale);
     VLTR_LAUNCH_CHECK("opt_attention");
     if (c.do_layer_norm_before) {
       // h = h + out_proj(att)
       if ((rc = gemm(att, w.out_w[L], h, w.out_b[L], h, M, H, H, 0, dt, s))) return rc;
-      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(h, x, (const T*)w.ln2_w[L], (const T*)w.ln2_b[L],
+      launch(layernorm_kernel<T>, dim3(ln_grid), dim3(128), 0, s, h, x, (const T*)w.ln2_w[L], (const T*)w.ln2_b[L],
                                                   nullptr, M, H, 1e-5f, 0);
       VLTR_LAUNCH_CHECK("opt_layernorm");
       if ((rc = gemm(x, w.fc1_w[L], ff, w.fc1_b[L], nullptr, M, F, H, 1, dt, s))) return rc;
@@ -583,18 +597,18 @@ static int forward_t(const Model& mdl, const int32_t* ids, const int32_t* positi
     } else {
       // h = LN1(h + out_proj(att)); h = LN2(h + fc2(relu(fc1(h))))
       if ((rc = gemm(att, w.out_w[L], x, w.out_b[L], h, M, H, H, 0, dt, s))) return rc;
-      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(x, h, (const T*)w.ln1_w[L], (const T*)w.ln1_b[L],
+      launch(layernorm_kernel<T>, dim3(ln_grid), dim3(128), 0, s, x, h, (const T*)w.ln1_w[L], (const T*)w.ln1_b[L],
                                                   nullptr, M, H, 1e-5f, 0);
       VLTR_LAUNCH_CHECK("opt_layernorm");
       if ((rc = gemm(h, w.fc1_w[L], ff, w.fc1_b[L], nullptr, M, F, H, 1, dt, s))) return rc;
       if ((rc = gemm(ff, w.fc2_w[L], x, w.fc2_b[L], h, M, H, F, 0, dt, s))) return rc;
-      layernorm_kernel<T><<<ln_grid, 128, 0, s>>>(x, h, (const T*)w.ln2_w[L], (const T*)w.ln2_b[L],
+      launch(layernorm_kernel<T>, dim3(ln_grid), dim3(128), 0, s, x, h, (const T*)w.ln2_w[L], (const T*)w.ln2_b[L],
                                                   nullptr, M, H, 1e-5f, 0);
       VLTR_LAUNCH_CHECK("opt_layernorm");
     }
   }
   // last token of every prompt -> final LN (row-wise, so only those rows are normalised)
-  layernorm_kernel<T><<<(P + 3) / 4, 128, 0, s>>>(h, last, (const T*)w.final_ln_w,
+  launch(layernorm_kernel<T>, dim3((P + 3) / 4), dim3(128), 0, s, h, last, (const T*)w.final_ln_w,
                                                   (const T*)w.final_ln_b, last_rows, P, H, 1e-5f,
                                                   c.final_layer_norm ? 0 : 1);
   VLTR_LAUNCH_CHECK("opt_final_layernorm");
@@ -603,7 +617,7 @@ static int forward_t(const Model& mdl, const int32_t* ids, const int32_t* positi
     if ((rc = gemm(last, w.project_out, last_e, nullptr, nullptr, P, E, H, 0, dt, s))) return rc;
     feat = last_e;
   }
-  score_kernel<T><<<(P * c.num_labels + 3) / 4, 128, 0, s>>>(feat, (const T*)w.score, logits, P,
+  launch(score_kernel<T>, dim3((P * c.num_labels + 3) / 4), dim3(128), 0, s, feat, (const T*)w.score, logits, P,
                                                              c.num_labels, E);
   VLTR_LAUNCH_CHECK("opt_score");
   return VLTR_OK;

@@ -157,6 +157,10 @@ def main():
             tune("attn_trace", 0)
             t = buf.cpu().numpy().reshape(nw, 16)
             t = t[t[:, 0] != 0]
+            if len(t) == 0:
+                print("   (no timeline: build the library with `make -C vllm_ltr_b200/csrc clean all "
+                      "EXTRA=-DVLTR_ATTN_TRACE=1`)")
+                continue
             t0 = t[:, 0].min()
             start, plan, first, end = (t[:, i] - t0 for i in range(4))
             worked = t[:, 5] > 0

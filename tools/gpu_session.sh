@@ -20,6 +20,8 @@ for s in $STEPS; do
     sweepattn) timeout 900 python tools/op_sweep.py --ops attn --json $OUT/sweep_attn.json > $OUT/sweep_attn.log 2>&1; echo "sweepattn rc=$?"; cat $OUT/sweep_attn.log ;;
     ncumma)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 3 -c 1 -f -o $OUT/attn_mma_prof python tools/op_sweep.py --ops attn --only 8b-gqa-bf16:256:trace:v1 > $OUT/ncumma.log 2>&1; echo "ncumma rc=$?"; tail -3 $OUT/ncumma.log
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 3 -c 1 -f -o $OUT/attn_tp8_prof python tools/op_sweep.py --ops attn --only 70b-tp8-bf16:256:512:v1 > $OUT/ncutp8.log 2>&1; echo "ncutp8 rc=$?"; tail -3 $OUT/ncutp8.log ;;
+    sweepsampler) timeout 600 python tools/op_sweep.py --ops sampler --json $OUT/sweep_sampler.json > $OUT/sweep_sampler.log 2>&1; echo "sweepsampler rc=$?"; cat $OUT/sweep_sampler.log ;;
+    sweepsmall) timeout 600 python tools/op_sweep.py --ops rms,silu,rope,cache --json $OUT/sweep_small.json > $OUT/sweep_small.log 2>&1; echo "sweepsmall rc=$?"; cat $OUT/sweep_small.log ;;
     sweeppred) timeout 600 python tools/op_sweep.py --ops gemm,predictor --json $OUT/sweep_pred.json > $OUT/sweep_pred.log 2>&1; echo "sweeppred rc=$?"; cat $OUT/sweep_pred.log ;;
     ncugemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 20 -c 3 -f -o $OUT/gemm_prof python tools/op_sweep.py --ops gemm > $OUT/ncugemm.log 2>&1; echo "ncugemm rc=$?"; tail -3 $OUT/ncugemm.log ;;
     prefilltests) timeout 900 python -m pytest tests/test_gpu_prefill.py tests/test_gpu_properties.py -q --maxfail=20 -p no:cacheprovider > $OUT/prefilltests.log 2>&1; echo "prefilltests rc=$?"; tail -25 $OUT/prefilltests.log ;;

@@ -214,6 +214,28 @@ def main():
         ours = timeit(lambda: _C.cache_ops.copy_blocks(ks, vs, mapping), iters=10)
         rr = timeit(lambda: ref.cache_ops.copy_blocks(ks, vs, mapping), iters=10) if ref else None
         report("copy_blocks", "32 layers x 64 pairs x 128 KiB", byts, ours, rr)
+    if "sampler" in ops_sel:
+        # next-token sampling: ours (one kernel) next to the reference's tensor program
+        # (sampler.py:67-80, :333-357, :528-544) written with the same torch calls
+        from vllm_ltr_b200.sampler import sample_rows
+        for R, V, dt in ((256, 32000, torch.float16), (256, 128256, torch.bfloat16),
+                         (64, 128256, torch.bfloat16), (8, 32000, torch.float16)):
+            lg = (torch.randn(R, V, generator=g, device=DEV) * 3).to(dt)
+            rnd = torch.ones(R, dtype=torch.uint8, device=DEV)
+
+            def ref_prog():
+                x = lg.clone()
+                x.div_(torch.ones(R, 1, dtype=dt, device=DEV))
+                probs = torch.softmax(x, dim=-1, dtype=torch.float)
+                logprobs = torch.log_softmax(x, dim=-1, dtype=torch.float)
+                q = torch.empty_like(probs).exponential_()
+                tok = probs.div_(q).argmax(dim=1)
+                lp = logprobs[torch.arange(R, device=DEV), tok]
+                return tok, lp, (logprobs > lp[:, None]).long().sum(1).add_(1)
+            ours = timeit(lambda: sample_rows(lg, None, rnd, None, seed=1, offset=0))
+            rr = timeit(ref_prog)
+            report("sampler", f"rows={R} vocab={V} {str(dt).split('.')[-1]} random", R * V * lg.element_size(),
+                   ours, rr)
     if "gemm" in ops_sel:
         # the predictor's dense layers: ours (tcgen05) next to cuBLAS (torch.nn.functional.linear)
         from vllm_ltr_b200 import predictor as P

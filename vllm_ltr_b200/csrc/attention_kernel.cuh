@@ -75,6 +75,11 @@ struct Params {
   int* tickets;                 // [num_seqs * passes * num_kv_heads] partition tickets, all zero
   long long* trace;             // development: 16 stamps per warp (tools/attn_tune.py) or null
 };
+// per-warp timeline for tools/attn_tune.py --trace: build with `make EXTRA=-DVLTR_ATTN_TRACE=1`
+// (kept out of the production build: the extra live state costs registers in the tile loop)
+#ifndef VLTR_ATTN_TRACE
+#define VLTR_ATTN_TRACE 0
+#endif
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -345,61 +350,28 @@ __device__ __forceinline__ float4 load_cg_4(const void* base, int64_t elem, bool
   }
 }
 
-template <typename T, int D, int HM>
+template <typename T, int D>
 __device__ __forceinline__ void merge_partials(const Params& p, int seq, int head0, int nheads,
                                                int np, int lane) {
-  constexpr int HB = HM < 4 ? HM : 4, JB = 4;
+  constexpr int HB = 4, JB = 4;
   constexpr int NV = (D + 127) / 128;   // 4-element vectors per lane
-  // Weights first.  Up to 32 partitions (always, for v1: <= 16 per sequence) lane j owns partition
-  // j: the (max, exp_sum) pairs of ALL heads are fetched in one round trip to L2 and turned into
-  // normalised weights with shuffles; the accumulation below then only waits for tmp_out rows.
-  const bool lanes_own = np <= 32;
-  float wreg[HM];
-#pragma unroll
-  for (int h = 0; h < HM; ++h) wreg[h] = 0.f;
-  if (lanes_own) {
-    float ml[HM], es[HM];
-#pragma unroll
-    for (int h = 0; h < HM; ++h) {
-      const bool ok = h < nheads && lane < np;
-      const int64_t idx = ((int64_t)seq * p.num_heads + head0 + (h < nheads ? h : 0)) * p.n_part +
-                          (lane < np ? lane : 0);
-      ml[h] = ok ? __ldcg(p.max_logits + idx) : -INFINITY;
-      es[h] = ok ? __ldcg(p.exp_sums + idx) : 0.f;
-    }
-#pragma unroll
-    for (int h = 0; h < HM; ++h) {
-      if (h < nheads) {      // warp-uniform
-        float m = ml[h];
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float e = lane < np ? es[h] * expf(ml[h] - m) : 0.f;
-        float sum = e;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        wreg[h] = e * __fdividef(1.0f, sum + 1e-6f);
-      }
-    }
-  }
   for (int h0 = 0; h0 < nheads; h0 += HB) {
     float mx[HB], inv[HB];
-    if (!lanes_own) {
 #pragma unroll
-      for (int hh = 0; hh < HB; ++hh) {
-        const int h = min(h0 + hh, nheads - 1);
-        const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
-        float m = -INFINITY;
-        for (int j = lane; j < np; j += 32) m = fmaxf(m, __ldcg(p.max_logits + base + j));
+    for (int hh = 0; hh < HB; ++hh) {
+      const int h = min(h0 + hh, nheads - 1);
+      const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
+      float m = -INFINITY;
+      for (int j = lane; j < np; j += 32) m = fmaxf(m, __ldcg(p.max_logits + base + j));
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float sum = 0.f;
-        for (int j = lane; j < np; j += 32)
-          sum += __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - m);
+      for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int j = lane; j < np; j += 32)
+        sum += __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - m);
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        mx[hh] = m;
-        inv[hh] = __fdividef(1.0f, sum + 1e-6f);
-      }
+      for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mx[hh] = m;
+      inv[hh] = __fdividef(1.0f, sum + 1e-6f);
     }
     float4 a[HB][NV];
 #pragma unroll
@@ -416,31 +388,15 @@ __device__ __forceinline__ void merge_partials(const Params& p, int seq, int hea
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
           const int j = min(j0 + jj, np - 1);
+          w[hh][jj] = j0 + jj < np ? __ldcg(p.exp_sums + base + j) *
+                                         expf(__ldcg(p.max_logits + base + j) - mx[hh]) * inv[hh]
+                                   : 0.f;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
             const int d = 4 * lane + 128 * i;
             v[hh][jj][i] = (D % 128 == 0 || d < D)
                                ? load_cg_4<T>(p.tmp_out, (base + j) * D + d, p.tmp_is_f32 != 0)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (!lanes_own)
-            w[hh][jj] = j0 + jj < np ? __ldcg(p.exp_sums + base + j) *
-                                           expf(__ldcg(p.max_logits + base + j) - mx[hh]) * inv[hh]
-                                     : 0.f;
-        }
-      }
-      if (lanes_own) {
-        // weight of (head h0+hh, partition j0+jj) lives in lane j0+jj's wreg[h0+hh]
-#pragma unroll
-        for (int hh = 0; hh < HB; ++hh) {
-          float mine = 0.f;
-#pragma unroll
-          for (int h = 0; h < HM; ++h)
-            if (h == h0 + hh) mine = wreg[h];     // register select (h0 is a multiple of HB)
-#pragma unroll
-          for (int jj = 0; jj < JB; ++jj) {
-            const float x = __shfl_sync(0xffffffffu, mine, (j0 + jj) & 31);
-            w[hh][jj] = (j0 + jj < np && h0 + hh < nheads) ? x : 0.f;
           }
         }
       }
@@ -573,7 +529,11 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int S = p.stages;
+#if VLTR_ATTN_TRACE
   long long* tr = p.trace != nullptr ? p.trace + ((int64_t)blockIdx.x * nwarps + warp) * 16 : nullptr;
+#else
+  constexpr long long* tr = nullptr;   // tracing compiled out: every `if (tr != nullptr)` folds away
+#endif
   if (tr != nullptr && lane == 0) tr[0] = gtime();
   int tr_items = 0, tr_tiles = 0;
   long long tr_wait = 0, tr_loop0 = 0, tr_loop = 0;
@@ -1185,7 +1145,7 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
       done = __shfl_sync(0xffffffffu, done, 0);
       if (done == cur.nparts - 1) {
         __threadfence();
-        merge_partials<T, D, GT>(p, seq, head0, nheads, cur.nparts, lane);
+        merge_partials<T, D>(p, seq, head0, nheads, cur.nparts, lane);
         if (lane == 0) p.tickets[gid] = 0;   // leave the ticket table clean for the next launch
       }
     }

@@ -29,7 +29,9 @@ import os
 import time
 import types
 from collections import deque
-from typing import Dict, List, Optional
+from itertools import compress, islice
+from operator import itemgetter
+from typing import Dict, Iterable, List, Optional
 
 import numpy as np
 
@@ -74,14 +76,20 @@ def _ref():
 # _get_ordered_requests for schedule_type "opt*"        (scheduler.py:969-1000)
 # ---------------------------------------------------------------------------------------------
 def get_opt_ordered_requests(self) -> list:
-    unscored = [r for r in self.waiting if r.need_aux_model_score()]
+    # need_aux_model_score() is `aux_model_score is None` (vllm/sequence.py:460-461): read the
+    # attribute directly, the scan touches every waiting request every tick
+    unscored = [r for r in self.waiting if r.aux_model_score is None]
     if unscored:
         timed = int(os.environ.get("OPT_TIME", 0))
         t0 = time.time() if timed else 0.0
         self.aux_model.obtain_aux_scores(unscored)
         if timed:
             print("OPT-TIME: ", time.time() - t0)
-    live = list(self.waiting) + list(self.running) + list(self.swapped)
+    live = list(self.waiting)
+    nw = len(live)
+    live.extend(self.running)
+    nr = len(live) - nw
+    live.extend(self.swapped)
     pri = None
     if self.starv != -1:
         # starvation control: a request idle for `starv` ticks is promoted for `period`
@@ -93,7 +101,15 @@ def get_opt_ordered_requests(self) -> list:
                 r.pri = 0
         pri = [r.pri for r in live]
     order = self._vltr_ranker.order([r.aux_model_score for r in live], pri, negate=True)
-    return [live[i] for i in order.tolist()]
+    n = len(live)
+    if n >= 2:
+        ordered = list(itemgetter(*order.tolist())(live))
+    else:
+        ordered = list(live)
+    # remembered for general_schedule: which queue every rank came from is a range test on the
+    # permutation (live = waiting ++ running ++ swapped), no per-request lookups
+    self._vltr_tick = (ordered, live, order, nw, nr)
+    return ordered
 
 
 def update_opt_priority(self) -> None:     # scheduler.py:1002-1003
@@ -103,12 +119,17 @@ def update_opt_priority(self) -> None:     # scheduler.py:1002-1003
 # ---------------------------------------------------------------------------------------------
 # reserve_free_blocks                                    (scheduler.py:1376-1502)
 # ---------------------------------------------------------------------------------------------
-def _reserve_free_blocks(self, S, blocks_needed: int, pinned: list, rest: list,
+def _reserve_free_blocks(self, S, blocks_needed: int, pinned: list,
+                         evict_candidates: Iterable, swapin_candidates: Iterable,
                          where: Dict[int, int], dropped_running: set, final_budget):
     """Make room for the pinned (selected) requests: swap out from the tail of the rank order,
     then from the tail of the pinned list; otherwise swap in the best-ranked swapped requests.
-    `where` maps id(request) -> queue at the start of the tick; requests preempted here are
-    recorded in `dropped_running` (they leave self.running).  Returns
+    `evict_candidates`: the members of the running queue among the unselected requests, LOWEST
+    rank first; `swapin_candidates`: the members of the swapped queue among them, best rank first
+    (the reference walks all unselected requests and skips the others, :1402-1416 / :1459-1499).
+    `where` maps id(request) -> queue at the start of the tick for running / swapped requests
+    (waiting ones are absent); requests preempted here are recorded in `dropped_running` (they
+    leave self.running).  Returns
     (execute, preempted, swapped_out, blocks_to_swap_out, blocks_to_swap_in)."""
     bm = self.block_manager
     RUNNING, SWAPPED = S.SequenceStatus.RUNNING, S.SequenceStatus.SWAPPED
@@ -124,14 +145,12 @@ def _reserve_free_blocks(self, S, blocks_needed: int, pinned: list, rest: list,
         (preempted if mode == S.PreemptionMode.RECOMPUTE else swapped_out).append(req)
 
     if must_swap_out:
-        pinned_ids = {r.request_id for r in pinned}
-        for req in reversed(rest):                      # lowest rank first
-            assert req.request_id not in pinned_ids
+        for req in evict_candidates:                    # lowest rank first
             if shortfall <= 0:
                 break
             # only members of the running queue can hold RUNNING sequences (waiting / swapped
-            # requests hold WAITING / SWAPPED ones): the id lookup skips the per-request scan
-            if where.get(id(req)) == _RUNNING and req.get_seqs(status=RUNNING):
+            # requests hold WAITING / SWAPPED ones)
+            if req.get_seqs(status=RUNNING):
                 shortfall -= len(bm._get_physical_blocks(req))
                 evict(req)
                 if where.get(id(req)) == _RUNNING and id(req) not in dropped_running:
@@ -164,8 +183,8 @@ def _reserve_free_blocks(self, S, blocks_needed: int, pinned: list, rest: list,
     if not must_swap_out:
         # proactive swap-in, best rank first, while blocks (shortfall is <= 0 here: the spare
         # room) and the final budget allow
-        for req in rest:
-            if where.get(id(req)) != _SWAPPED or not req.get_seqs(status=SWAPPED):
+        for req in swapin_candidates:
+            if not req.get_seqs(status=SWAPPED):
                 continue
             new_seqs = req.get_max_num_running_seqs()
             new_tokens = self._get_num_new_tokens(req, SWAPPED, enable_chunking=True,

@@ -34,14 +34,17 @@ for s in $STEPS; do
     tuneq)   timeout 600 python tools/attn_tune.py --trace --json $OUT/attn_tuneq.json > $OUT/attn_tuneq.log 2>&1; echo "tuneq rc=$?"; cat $OUT/attn_tuneq.log ;;
     benchab) timeout 600 python bench.py --no-pdl --launch eager --no-cpu-baseline > $OUT/bench_nopdl_eager.json 2> $OUT/bench_ab.err; echo "benchab rc=$?"; cat $OUT/bench_nopdl_eager.json ;;
     benchmodels) for m in llama-3-8b llama-3-8b-fp8kv; do timeout 600 python bench.py --model $m --no-cpu-baseline > $OUT/bench_$m.json 2> $OUT/bench_$m.err; echo "bench $m rc=$?"; cat $OUT/bench_$m.json; done ;;
+    ncusampler) timeout 600 ncu --set full --clock-control none --import-source on -k regex:sample_kernel -s 3 -c 2 -f -o $OUT/sampler_prof python tools/op_sweep.py --ops sampler > $OUT/ncusampler.log 2>&1; echo "ncusampler rc=$?"; tail -3 $OUT/ncusampler.log ;;
+    ncugqa)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_gqa_prof python bench.py --model llama-3-8b --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncugqa.log 2>&1; echo "ncugqa rc=$?"; tail -2 $OUT/ncugqa.log
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_fp8_prof python bench.py --model llama-3-8b-fp8kv --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncufp8.log 2>&1; echo "ncufp8 rc=$?"; tail -2 $OUT/ncufp8.log ;;
     golden)  timeout 600 python tests/golden/gen_golden_cuda.py $OUT/ref_cuda.npz > $OUT/golden.log 2>&1; echo "golden rc=$?"; tail -2 $OUT/golden.log ;;
     bench)   timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "benchref rc=$?"; cat $OUT/bench_ref.json ;;
     sweep)   timeout 1200 python tools/op_sweep.py --json $OUT/sweep.json > $OUT/sweep.log 2>&1; echo "sweep rc=$?"; cat $OUT/sweep.log ;;
     sweepq)  timeout 600 python tools/op_sweep.py --quick --ops attn --json $OUT/sweepq.json > $OUT/sweepq.log 2>&1; echo "sweepq rc=$?"; cat $OUT/sweepq.log ;;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline > $OUT/launches.log 2>&1; echo "launches rc=$?"; tail -2 $OUT/launches.log ;;
-    ncusmall) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"reshape_and_cache|rms_vec|act_vec|rope_neox|reduce_kernel" -s 40 -c 10 -f -o $OUT/small_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline > $OUT/ncusmall.log 2>&1; echo "ncusmall rc=$?"; tail -2 $OUT/ncusmall.log ;;
-    ncu)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline > $OUT/ncu.log 2>&1; echo "ncu rc=$?"; tail -2 $OUT/ncu.log ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/launches.log 2>&1; echo "launches rc=$?"; tail -2 $OUT/launches.log ;;
+    ncusmall) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"reshape_and_cache|rms_vec|act_vec|rope_neox|reduce_kernel" -s 40 -c 10 -f -o $OUT/small_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncusmall.log 2>&1; echo "ncusmall rc=$?"; tail -2 $OUT/ncusmall.log ;;
+    ncu)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncu.log 2>&1; echo "ncu rc=$?"; tail -2 $OUT/ncu.log ;;
   esac
 done
 echo "=== done $(date +%T)"

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Scheduler tick cost: reference Scheduler._general_schedule vs the plugin's host logic, pure
 Python on one core, at N live requests (baseline 3).  Needs /root/reference.
-The CUDA ranker is replaced by Python `sorted` here (no GPU in the build container); on the GPU box
-the rank itself costs ~0.1 ms at N = 10^4 (tools/op_sweep.py / bench.py tick_ms_alone).
+The CUDA ranker is replaced by a numpy stable argsort here (no GPU in the build container; same
+order as Python `sorted`, asserted); its time is reported separately - on the GPU box the rank
+kernel call costs ~0.3 ms at N = 10^4 (bench.py tick_ms_alone minus the predictor).
 
     python tools/sched_tick_bench.py > profiles/r01_scheduler_tick.txt
 """
@@ -26,6 +27,21 @@ from vllm.sequence import Logprob, Sequence, SequenceGroup, SequenceStatus  # no
 from vllm_ltr_b200 import ltr_scheduler  # noqa: E402
 
 
+class NumpyRanker:
+    """Stable order of (pri, -score): what the CUDA rank kernel returns (tests/test_gpu_ltr.py)."""
+    seconds = 0.0
+
+    def order(self, scores, pri=None, negate=True):
+        t0 = time.perf_counter()
+        key = -np.asarray(scores, dtype=np.float64) if negate else np.asarray(scores, dtype=np.float64)
+        if pri is None:
+            idx = np.argsort(key, kind="stable")
+        else:
+            idx = np.lexsort((key, np.asarray(pri)))       # last key is the primary one; stable
+        NumpyRanker.seconds += time.perf_counter() - t0
+        return idx.astype(np.int32)
+
+
 def build(n, plugin):
     sc = SchedulerConfig(768, 256, 8192, enable_chunked_prefill=True, schedule_type="opt-xxx")
     cc = CacheConfig(16, 1.0, 1, "auto")
@@ -35,7 +51,7 @@ def build(n, plugin):
     score = rng.normal(0, 1, n).astype(np.float16).astype(float)
     s.aux_model = R.StubScorer({str(i): float(score[i]) for i in range(n)})
     if plugin:
-        ltr_scheduler.install(s, ranker=R.PythonRanker())
+        ltr_scheduler.install(s, ranker=NumpyRanker())
     for i in range(n):
         toks = list(range(int(rng.integers(4, 200))))
         s.add_seq_group(SequenceGroup(str(i), [Sequence(i, "", toks, 16)],
@@ -53,7 +69,7 @@ def tick(s):
     return o
 
 
-print("N live requests | reference ms/tick | plugin host logic ms/tick | identical decisions")
+print("N live requests | reference ms/tick | plugin host logic ms/tick (of which stand-in ranker) | identical decisions")
 for n in (256, 2000, 10000):
     res = {}
     for plugin in (False, True):
@@ -62,6 +78,7 @@ for n in (256, 2000, 10000):
         for _ in range(20):
             outs.append([(x.seq_group.request_id, x.token_chunk_size) for x in tick(s).scheduled_seq_groups])
         ts = []
+        NumpyRanker.seconds = 0.0
         for _ in range(8):
             t0 = time.perf_counter()
             o = s._schedule()     # the tick proper (metadata building in schedule() is outside the path)
@@ -73,5 +90,6 @@ for n in (256, 2000, 10000):
                     for seq in x.seq_group.get_seqs(status=SequenceStatus.RUNNING):
                         seq.append_token_id(7, {7: Logprob(0.0)})
             outs.append([(x.seq_group.request_id, x.token_chunk_size) for x in o.scheduled_seq_groups])
-        res[plugin] = (float(np.median(ts)) * 1e3, outs)
-    print(f"{n:>15d} | {res[False][0]:>17.2f} | {res[True][0]:>25.2f} | {res[False][1] == res[True][1]}")
+        res[plugin] = (float(np.median(ts)) * 1e3, outs, NumpyRanker.seconds / 8 * 1e3)
+    print(f"{n:>15d} | {res[False][0]:>17.2f} | {res[True][0]:>25.2f} ({res[True][2]:.2f}) | "
+          f"{res[False][1] == res[True][1]}")

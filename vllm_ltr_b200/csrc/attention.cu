@@ -160,7 +160,7 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     // tail), at least 64 tokens, and no more than 16 partitions per sequence (the merge of a
     // sequence is done by one warp)
     const long long slots =
-        (long long)num_sms() * (g_tune.attn_slots > 0 ? g_tune.attn_slots : 8);
+        (long long)num_sms() * (g_tune.attn_slots > 0 ? g_tune.attn_slots : 12);
     const long long floor_tokens = g_tune.attn_min_tokens > 0 ? g_tune.attn_min_tokens : 64;
     const long long cap_tokens = g_tune.attn_cap_tokens > 0 ? g_tune.attn_cap_tokens : 512;
     const long long groups = (long long)num_seqs * num_kv_heads * p.passes;

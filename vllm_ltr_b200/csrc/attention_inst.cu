@@ -23,9 +23,10 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    // Resident warps per SM matter more than ring depth (measured, tools/attn_tune.py): three
-    // 4-warp CTAs with a 2-deep ring beat two with a 3-deep ring by 5-7% on 2-byte caches, and
-    // the e5m2 path (more instructions per byte: byte-permute conversions) wants four.
+    // Resident warps per SM matter more than ring depth when the queue is long (measured,
+    // tools/attn_tune.py): three 4-warp CTAs with a 2-deep ring beat two with a 3-deep ring by
+    // 5-10% on 2-byte caches.  The e5m2 tiles are half the size: sized for four CTAs (2-deep
+    // ring) - registers admit three, and the shallow ring measured fastest for them.
     const int ctas = want_ctas > 0 ? want_ctas : (C::FP8 ? 4 : 3);
     int budget = sm_smem / ctas - 1024 - kPlanBytes;       // 1 KiB per CTA is reserved by the system
     if (budget > max_optin - kPlanBytes) budget = max_optin - kPlanBytes;
@@ -55,14 +56,25 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
     pl.ok = true;
     return pl;
   };
-  static Plan dflt = make_plan(0, 0, 0);
+  // two plans: `thr` for long queues (throughput: most resident warps), `lat` for launches whose
+  // work items cannot even occupy the resident warps twice (small batches, tensor-parallel
+  // shards): there every warp streams one item at the latency-bound rate of its ring, and the
+  // deeper ring of two CTAs per SM wins (B=64 GQA: 40 vs 47 us)
+  auto set_attr = [&](const Plan& a, const Plan& b) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         a.smem > b.smem ? a.smem : b.smem);
+  };
+  static Plan thr = make_plan(0, 0, 0), lat = make_plan(0, 0, 2);
+  static bool attr_ready = (set_attr(thr, lat), true);
+  (void)attr_ready;
   const bool tuned = g_tune.attn_warps > 0 || g_tune.attn_stages > 0 || g_tune.attn_ctas > 0;
   static bool was_tuned = false;
   if (!tuned && was_tuned) {       // back from a development override: restore the attribute
-    dflt = make_plan(0, 0, 0);
+    set_attr(thr, lat);
     was_tuned = false;
   }
-  Plan plan = dflt;
+  const long long items_ub = (long long)p0.num_seqs * p0.n_part * p0.passes * p0.num_kv_heads;
+  Plan plan = (lat.ok && items_ub < 2LL * num_sms() * thr.ctas_per_sm * thr.warps) ? lat : thr;
   if (tuned) {
     plan = make_plan((int)g_tune.attn_warps, (int)g_tune.attn_stages, (int)g_tune.attn_ctas);
     was_tuned = true;
@@ -71,7 +83,6 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
   Params p = p0;
   p.stages = plan.stages;
   int grid = num_sms() * plan.ctas_per_sm;
-  const long long items_ub = (long long)p.num_seqs * p.n_part * p.passes * p.num_kv_heads;
   const long long need = (items_ub + plan.warps - 1) / plan.warps;
   if (grid > need) grid = (int)need;
   if (grid < 1) grid = 1;

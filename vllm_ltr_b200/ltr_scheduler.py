@@ -11,12 +11,13 @@ against ``/root/reference/vllm/core/scheduler.py``), but
 
 * the queue sort runs on the GPU (``vltr_ltr_rank_host``, csrc/ltr_rank.cu) instead of Python's
   ``sorted`` over key tuples, and
-* the bookkeeping around it is linear in the number of live requests: the reference scans deques
-  for membership (``x in deque``, :1139/:1166/:1187), removes the selected requests one
-  ``list.remove`` at a time (:1213-1214) and tests every live request against the list of
-  scheduled ones (:1358-1365) - about 140 ms per tick at 10 000 live requests.  Here membership
-  is an id-keyed dict built once per tick, the selected requests are a prefix of the order, and
-  the queues are rebuilt in one pass.
+* the bookkeeping around it is linear in the number of live requests with a small constant: the
+  reference scans deques for membership (``x in deque``, :1139/:1166/:1187), removes the selected
+  requests one ``list.remove`` at a time (:1213-1214) and tests every live request against the
+  list of scheduled ones (:1358-1365) - about 100-140 ms per tick at 10 000 live requests.  Here
+  only running / swapped requests (hundreds) are looked up by identity, the queue a rank came
+  from is a range test on the rank permutation, the selected requests are a prefix of the order,
+  and the waiting queue is rebuilt with one C-level ``compress``.
 
 Quirks of the reference that are part of its observable behaviour and therefore kept:
 * ties in (pri, -score) keep waiting -> running -> swapped deque order (stable sort);
@@ -228,17 +229,28 @@ def general_schedule(self):
                                 max_num_seqs=cfg.max_num_seqs)
     final_budget = S.SchedulingBudget(token_budget=cfg.max_num_batched_tokens,
                                       max_num_seqs=cfg.max_num_seqs)
-    where: Dict[int, int] = {}
-    for q, tag in ((self.waiting, _WAITING), (self.running, _RUNNING), (self.swapped, _SWAPPED)):
-        for r in q:
-            where[id(r)] = tag       # a request sits in exactly one queue
+    # which queue a request sits in.  Running and swapped requests (at most max_num_seqs plus
+    # whatever was preempted - hundreds) are looked up by identity; everything else in the order
+    # is a waiting request.  When the order came from get_opt_ordered_requests the ranks of the
+    # running / swapped requests are also known from the permutation itself (range tests on the
+    # indices into waiting ++ running ++ swapped), so no pass over the ~10^4 waiting requests is
+    # needed anywhere below.
+    tick = getattr(self, "_vltr_tick", None)
+    fast = tick is not None and tick[0] is ordered and len(ordered) == live_before
+    where: Dict[int, int] = {id(r): _RUNNING for r in self.running}
+    for r in self.swapped:
+        where[id(r)] = _SWAPPED
+    if not fast:
+        for r in self.waiting:
+            where[id(r)] = _WAITING
+    default_tag = _WAITING if fast else None
 
     # ---- admit in rank order until a budget runs out: the selection is a prefix of the order
     bm = self.block_manager
     blocks_needed = 0
     k = 0
     for req in ordered:
-        tag = where.get(id(req))
+        tag = where.get(id(req), default_tag)
         if tag == _RUNNING:
             new_tokens = self._get_num_new_tokens(req, RUNNING, True, budget)
             if new_tokens == 0:
@@ -271,11 +283,23 @@ def general_schedule(self):
         req.num_new_tokens, req.num_new_seqs = new_tokens, new_seqs
         blocks_needed += blocks
         k += 1
-    selected, rest = ordered[:k], ordered[k:]
+    selected = ordered[:k]
+    if fast:
+        _, live, order, nw, nr = tick
+        tail = order[k:]
+        run_ranks = np.flatnonzero((tail >= nw) & (tail < nw + nr))
+        swp_ranks = np.flatnonzero(tail >= nw + nr)
+        evict_candidates = (ordered[k + i] for i in run_ranks[::-1].tolist())
+        swapin_candidates = (ordered[k + i] for i in swp_ranks.tolist())
+    else:
+        rest = ordered[k:]
+        evict_candidates = (r for r in reversed(rest) if where.get(id(r)) == _RUNNING)
+        swapin_candidates = (r for r in rest if where.get(id(r)) == _SWAPPED)
 
     dropped_running: set = set()      # ids leaving self.running by preemption
     execute, preempted, swapped_out, to_swap_out, to_swap_in = _reserve_free_blocks(
-        self, S, blocks_needed, selected, rest, where, dropped_running, final_budget)
+        self, S, blocks_needed, selected, evict_candidates, swapin_candidates, where,
+        dropped_running, final_budget)
 
     # ---- allocate / append slots for what really executes -------------------------------------
     to_copy: Dict[int, List[int]] = {}
@@ -283,7 +307,7 @@ def general_schedule(self):
     taken = {_WAITING: set(), _RUNNING: set(), _SWAPPED: set()}
     SSG = S.ScheduledSequenceGroup
     for req in execute:
-        tag = where.get(id(req))
+        tag = where.get(id(req), default_tag)
         if tag == _RUNNING and id(req) in dropped_running:
             tag = None
         if tag is None or id(req) in taken[tag]:
@@ -314,7 +338,17 @@ def general_schedule(self):
 
     # ---- rebuild the three queues in one pass each ----------------------------------------------
     gone_w, gone_r, gone_s = taken[_WAITING], taken[_RUNNING] | dropped_running, taken[_SWAPPED]
-    waiting = deque(r for r in self.waiting if id(r) not in gone_w)
+    if not gone_w:
+        waiting = deque(self.waiting)
+    elif fast:
+        # the admitted waiting requests sit at known positions of the old queue: order[rank]
+        keep = bytearray(b"\x01") * nw
+        for rank, req in enumerate(selected):
+            if id(req) in gone_w:
+                keep[order[rank]] = 0
+        waiting = deque(compress(islice(live, nw), keep))
+    else:
+        waiting = deque(r for r in self.waiting if id(r) not in gone_w)
     waiting.extendleft(preempted)
     running = deque(r for r in self.running if id(r) not in gone_r)
     for group in (new_prefill, run_decode, run_prefill, swp_decode, swp_prefill):
@@ -338,15 +372,16 @@ def general_schedule(self):
         allow_both_swap=True,
     )
     # ---- idle / runs bookkeeping for every live request ----------------------------------------
-    ran = {id(s.seq_group) for s in out.scheduled_seq_groups}
+    # (scheduler.py:1358-1365: a request that ran has idle = 0 and, while promoted, one run less;
+    # every other live request has been idle one tick more)
     for q in (swapped, running, waiting):
         for r in q:
-            if id(r) in ran:
-                if r.pri == -1:
-                    r.runs -= 1
-                r.idle = 0
-            else:
-                r.idle += 1
+            r.idle += 1
+    for sg in out.scheduled_seq_groups:
+        r = sg.seq_group
+        if r.pri == -1:
+            r.runs -= 1
+        r.idle = 0
     return out
 
 

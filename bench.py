@@ -475,9 +475,10 @@ def _main(out):
     # N=1: the step is recorded once into a CUDA graph over static device inputs (the launch
     # mode a latency-sensitive caller uses; PDL edges between the kernels are kept by the graph).
     # `value` replays it with the inputs resident; the e2e leg copies the host buffers into the
-    # static inputs, replays, and reads the result back.  N>1 issues kernel by kernel (the fused
-    # exchange takes its barrier epoch as a launch argument).
-    use_graph = world == 1 and args.launch == "graph"
+    # static inputs, replays, and reads the result back.  N>1 with the fused exchange replays
+    # too (every rank in lockstep; the exchange kernels count their barrier epochs on the device);
+    # with --tp-exchange nccl the step is issued kernel by kernel.
+    use_graph = args.launch == "graph" and (world == 1 or args.tp_exchange == "fused")
     graph = graph_out = None
     launches_per_graph = 0
     if use_graph:

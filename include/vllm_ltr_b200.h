@@ -231,8 +231,11 @@ int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias, const
  * fp32 accumulation in rank order, results identical on all ranks. */
 typedef struct vltr_tp_comm {
   int rank, world;
-  uint32_t epoch;                 /* 2 * k + 1 for the k-th exchange on these buffers (k = 0, 1, ...):
-                                     every rank passes the same value, strictly increasing */
+  uint32_t epoch;                 /* 0: the kernels keep the exchange count in the signal pad
+                                     themselves (launch arguments never change: CUDA-graph safe);
+                                     or 2 * k + 1 for the k-th exchange on these pads (k = 0, 1,
+                                     ...), the same value on every rank, strictly increasing.
+                                     One mode per set of signal pads. */
   const void* const* x_ptrs;
   void* const* out_ptrs;
   void* const* resid_ptrs;        /* may be NULL for vltr_tp_allreduce */

@@ -7,6 +7,18 @@ mkdir -p $OUT
 STEPS=${*:-smoke tests golden bench sweep launches ncu}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
 nproc >> $OUT/gpu.txt
+# ncu reports with imported source run to tens of MB and gpurun_out/ is capped at 64 MiB: keep the
+# CSV pages (what profiles/ is written from) and drop reports above 14 MB
+export_rep() {
+  local rep=$OUT/$1.ncu-rep
+  [ -f $rep ] || return 0
+  ncu -i $rep --page raw --csv > $OUT/$1.raw.csv 2>/dev/null
+  ncu -i $rep --page details --csv > $OUT/$1.details.csv 2>/dev/null
+  ncu -i $rep --page source --csv > $OUT/$1.source.csv 2>/dev/null
+  local sz=$(stat -c %s $rep)
+  if [ $sz -gt 14000000 ]; then rm -f $rep; echo "$1.ncu-rep: $sz bytes, dropped (CSV pages kept)"; fi
+  if [ -f $OUT/$1.source.csv ] && [ $(stat -c %s $OUT/$1.source.csv) -gt 8000000 ]; then gzip -f $OUT/$1.source.csv; fi
+}
 for s in $STEPS; do
   echo "=== $s $(date +%T)"
   case $s in
@@ -30,13 +42,17 @@ for s in $STEPS; do
     chain)   timeout 600 python tools/chain_bench.py --json $OUT/chain.json > $OUT/chain.log 2>&1; echo "chain rc=$?"; cat $OUT/chain.log ;;
     tune3)   timeout 900 python tools/attn_tune.py --grid r3 --trace --cases 70b-tp8-bf16:256:trace,8b-gqa-bf16:64:trace,8b-gqa-bf16:256:trace,7b-mha-bf16:64:trace --json $OUT/attn_tune3.json > $OUT/attn_tune3.log 2>&1; echo "tune3 rc=$?"; cat $OUT/attn_tune3.log ;;
     samplertests) timeout 600 python -m pytest tests/test_gpu_sampler.py -q -p no:cacheprovider > $OUT/samplertests.log 2>&1; echo "samplertests rc=$?"; tail -25 $OUT/samplertests.log ;;
+    tp2)     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/tp_check.py > $OUT/tp_check_n2.log 2>&1; echo "tp_check rc=$?"; tail -22 $OUT/tp_check_n2.log
+             timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --no-cpu-baseline > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench n2 rc=$?"; cat $OUT/bench_n2.json; tail -3 $OUT/bench_n2.err
+             timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --no-cpu-baseline --launch eager > $OUT/bench_n2_eager.json 2> $OUT/bench_n2_eager.err; echo "bench n2 eager rc=$?"; cat $OUT/bench_n2_eager.json
+             timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29614 bench.py --gpus 2 --model llama-2-70b --layers 20 --no-cpu-baseline > $OUT/bench_n2_70b20.json 2> $OUT/bench_n2_70b20.err; echo "bench n2 70b rc=$?"; cat $OUT/bench_n2_70b20.json ;;
     tune2)   timeout 900 python tools/attn_tune.py --grid r3 --trace --json $OUT/attn_tune2.json > $OUT/attn_tune2.log 2>&1; echo "tune2 rc=$?"; cat $OUT/attn_tune2.log ;;
     tuneq)   timeout 600 python tools/attn_tune.py --trace --json $OUT/attn_tuneq.json > $OUT/attn_tuneq.log 2>&1; echo "tuneq rc=$?"; cat $OUT/attn_tuneq.log ;;
     benchab) timeout 600 python bench.py --no-pdl --launch eager --no-cpu-baseline > $OUT/bench_nopdl_eager.json 2> $OUT/bench_ab.err; echo "benchab rc=$?"; cat $OUT/bench_nopdl_eager.json ;;
     benchmodels) for m in llama-3-8b llama-3-8b-fp8kv; do timeout 600 python bench.py --model $m --no-cpu-baseline > $OUT/bench_$m.json 2> $OUT/bench_$m.err; echo "bench $m rc=$?"; cat $OUT/bench_$m.json; done ;;
-    ncusampler) timeout 600 ncu --set full --clock-control none --import-source on -k regex:sample_kernel -s 3 -c 2 -f -o $OUT/sampler_prof python tools/op_sweep.py --ops sampler > $OUT/ncusampler.log 2>&1; echo "ncusampler rc=$?"; tail -3 $OUT/ncusampler.log ;;
-    ncugqa)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_gqa_prof python bench.py --model llama-3-8b --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncugqa.log 2>&1; echo "ncugqa rc=$?"; tail -2 $OUT/ncugqa.log
-             timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_fp8_prof python bench.py --model llama-3-8b-fp8kv --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncufp8.log 2>&1; echo "ncufp8 rc=$?"; tail -2 $OUT/ncufp8.log ;;
+    ncusampler) timeout 600 ncu --set full --clock-control none --import-source on -k regex:sample_kernel -s 3 -c 2 -f -o $OUT/sampler_prof python tools/op_sweep.py --ops sampler > $OUT/ncusampler.log 2>&1; echo "ncusampler rc=$?"; tail -3 $OUT/ncusampler.log; export_rep sampler_prof ;;
+    ncugqa)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_gqa_prof python bench.py --model llama-3-8b --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncugqa.log 2>&1; echo "ncugqa rc=$?"; tail -2 $OUT/ncugqa.log; export_rep attn_gqa_prof
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_fp8_prof python bench.py --model llama-3-8b-fp8kv --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncufp8.log 2>&1; echo "ncufp8 rc=$?"; tail -2 $OUT/ncufp8.log; export_rep attn_fp8_prof ;;
     golden)  timeout 600 python tests/golden/gen_golden_cuda.py $OUT/ref_cuda.npz > $OUT/golden.log 2>&1; echo "golden rc=$?"; tail -2 $OUT/golden.log ;;
     bench)   timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -3 $OUT/bench.err ;;
     benchref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "benchref rc=$?"; cat $OUT/bench_ref.json ;;
@@ -44,7 +60,7 @@ for s in $STEPS; do
     sweepq)  timeout 600 python tools/op_sweep.py --quick --ops attn --json $OUT/sweepq.json > $OUT/sweepq.log 2>&1; echo "sweepq rc=$?"; cat $OUT/sweepq.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/launches.log 2>&1; echo "launches rc=$?"; tail -2 $OUT/launches.log ;;
     ncusmall) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"reshape_and_cache|rms_vec|act_vec|rope_neox|reduce_kernel" -s 40 -c 10 -f -o $OUT/small_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncusmall.log 2>&1; echo "ncusmall rc=$?"; tail -2 $OUT/ncusmall.log ;;
-    ncu)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncu.log 2>&1; echo "ncu rc=$?"; tail -2 $OUT/ncu.log ;;
+    ncu)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 8 -c 2 -f -o $OUT/attn_prof python bench.py --steps 1 --warmup 3 --layers 4 --no-cpu-baseline --launch eager > $OUT/ncu.log 2>&1; echo "ncu rc=$?"; tail -2 $OUT/ncu.log; export_rep attn_prof ;;
   esac
 done
 echo "=== done $(date +%T)"

@@ -28,7 +28,8 @@ def main():
     ok = True
     for dtype in (torch.bfloat16, torch.float16):
         for T, H in ((1, 4096), (7, 4096), (256, 4096), (256, 8192), (768, 8192), (300, 5120)):
-            comm = FusedTPComm(768, H, dtype, dev)
+            # both epoch modes: counted by the kernels (default, graph-safe) / passed by the host
+            comm = FusedTPComm(768, H, dtype, dev, device_epoch=(T != 7))
             g = torch.Generator(device=dev).manual_seed(100 + rank)
             x = torch.randint(-4, 5, (T, H), generator=g, device=dev).to(dtype)
             g0 = torch.Generator(device=dev).manual_seed(7)
@@ -58,6 +59,47 @@ def main():
             if rank == 0:
                 print(f"{dtype} T={T} H={H}: resid exact={e_res} out maxdiff={diff:.3g} ok={e_out} plain exact={e_plain}", flush=True)
             del comm
+    # CUDA-graph replay of a chain of exchanges (device-side epochs): three replays must give
+    # what three eager rounds give
+    T, H, dtype = 256, 4096, torch.bfloat16
+    comm = FusedTPComm(256, H, dtype, dev)
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    xs = [torch.randint(-3, 4, (T, H), generator=g, device=dev).to(dtype) for _ in range(2)]
+    w = torch.ones(H, device=dev, dtype=dtype)
+
+    def chain():
+        comm.allreduce_add_rms_norm(0, w, 1e-5, T)
+        comm.allreduce_add_rms_norm(1, w, 1e-5, T)
+
+    def reset():
+        comm.x[0][:T].copy_(xs[0])
+        comm.x[1][:T].copy_(xs[1])
+        comm.resid[:T].zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    reset()
+    for _ in range(3):
+        chain()
+    torch.cuda.synchronize()
+    want_res, want_out = comm.resid[:T].clone(), comm.out[:T].clone()
+    reset()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        chain()                                   # warm-up round (counts as round 1)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        chain()
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    e_graph = torch.equal(comm.resid[:T], want_res) and torch.equal(comm.out[:T], want_out)
+    ok = ok and e_graph
+    if rank == 0:
+        print(f"graph replay of 2 exchanges x 2 (after 1 eager round): exact={e_graph}", flush=True)
+    del comm
     # timing at the decode shapes
     for T, H in ((256, 4096), (256, 8192), (768, 8192)):
         dtype = torch.bfloat16

@@ -32,7 +32,7 @@ constexpr int kMaxWorld = 8;
 constexpr int kPadBase = 1024;         // our flags start here (u32 index); torch's own barrier uses the front
 constexpr int kThreads = 256;
 // signal-pad layout (u32 index from kPadBase): [0..7] arrival epoch of rank p (written by p),
-// [9] local count of finished CTAs
+// [9] local count of finished CTAs, [10] this rank's exchange counter (device-epoch mode)
 
 struct Comm {
   const void* x[kMaxWorld];            // every rank's x buffer (index = rank)
@@ -40,7 +40,8 @@ struct Comm {
   void* resid[kMaxWorld];
   uint32_t* pad[kMaxWorld];            // every rank's signal pad
   int rank, world;
-  uint32_t epoch;                      // 2 * call_index + 1 (start barrier), + 2 (end barrier)
+  uint32_t epoch;                      // 2 * call_index + 1 (start barrier), + 1 (end barrier);
+                                       // 0: read it from this rank's counter in the signal pad
 };
 
 __device__ __forceinline__ void spin_trap() {
@@ -119,11 +120,17 @@ __global__ void __launch_bounds__(kThreads)
   const int cta = blockIdx.x;
   const int nvec = hidden / N;
   uint32_t* fin = c.pad[c.rank] + kPadBase + 9;
+  // Device-epoch mode (CUDA-graph safe: nothing in the launch arguments changes from call to
+  // call): the epoch is 1 + this rank's exchange counter, which the last CTA of every exchange
+  // advances by 2.  Every rank issues the same exchanges in the same order, so the counters
+  // agree.  All CTAs read it before any can finish (the advance waits for all of them).
+  uint32_t* ctr = c.pad[c.rank] + kPadBase + 10;
+  const uint32_t epoch = c.epoch != 0 ? c.epoch : *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
 
   // start: every rank's x is complete (its producing kernels finished before this one started).
   // CTA 0 announces this rank; every CTA polls the local pad for all peers' announcements.
-  if (cta == 0) announce(c, c.epoch);
-  wait_peers(c, c.epoch);
+  if (cta == 0) announce(c, epoch);
+  wait_peers(c, epoch);
 
   // rows owned by this rank: r, r + world, ...; CTAs of this rank stride over them
   for (int row = c.rank + cta * c.world; row < num_tokens; row += gridDim.x * c.world) {
@@ -221,8 +228,9 @@ __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
   if (s_last) {
-    announce(c, c.epoch + 1);
-    wait_peers(c, c.epoch + 1);
+    announce(c, epoch + 1);
+    wait_peers(c, epoch + 1);
+    if (c.epoch == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(ctr) = epoch + 1u;
   }
 }
 
@@ -266,8 +274,9 @@ static int run(const vltr_tp_comm* comm, const void* weight, float eps, int num_
   VLTR_CHECK(hidden % n == 0, VLTR_ERR_UNSUPPORTED,
              "tp_allreduce: hidden %d must be a multiple of %d", hidden, n);
   if (num_tokens == 0) return VLTR_OK;
-  VLTR_CHECK(comm->epoch % 2 == 1, VLTR_ERR_INVALID,
-             "tp_allreduce: epoch must be odd (2 * call_index + 1), got %u", comm->epoch);
+  VLTR_CHECK(comm->epoch == 0 || comm->epoch % 2 == 1, VLTR_ERR_INVALID,
+             "tp_allreduce: epoch must be 0 (device-side counter) or odd (2 * call_index + 1), "
+             "got %u", comm->epoch);
   Comm c{};
   c.rank = comm->rank;
   c.world = comm->world;

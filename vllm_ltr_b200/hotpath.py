@@ -172,10 +172,13 @@ class DecodeHotPath:
         attention partitions), so a graph is valid for contexts up to that bound - the engine
         keys its graphs the same way (model_runner.py:896-970 pads to the captured batch size and
         passes the model's max context length).  The first, uncaptured step lets the library
-        grow its workspaces; nothing allocates while recording.  Single-GPU only: the fused
-        tensor-parallel exchange takes its barrier epoch as a launch argument."""
-        if getattr(self, "comm", None) is not None:
-            raise RuntimeError("capture(): the fused tensor-parallel exchange is not graph-safe")
+        grow its workspaces; nothing allocates while recording.  With the fused tensor-parallel
+        exchange attached, every rank must capture and replay in lockstep (each replay is one
+        set of exchanges) and the communicator must count its epochs on the device."""
+        comm = getattr(self, "comm", None)
+        if comm is not None and not comm.device_epoch:
+            raise RuntimeError("capture(): FusedTPComm(device_epoch=False) passes the barrier "
+                               "epoch as a launch argument and cannot be replayed")
         assert self.attn_events is None
         args = (hidden_in, positions, slot_mapping, block_tables, context_lens, max_context_len)
         side = torch.cuda.Stream(device=self.device)

@@ -69,7 +69,8 @@ class FusedTPComm:
     pointers (plumbing only; the data path is the kernel in libvllm_ltr_b200)."""
 
     def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device,
-                 group: Optional[dist.ProcessGroup] = None, num_inputs: int = 2):
+                 group: Optional[dist.ProcessGroup] = None, num_inputs: int = 2,
+                 device_epoch: bool = True):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
@@ -98,6 +99,10 @@ class FusedTPComm:
                         ("resid_ptrs", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p)]
 
         addr = lambda a: ctypes.cast(a, ctypes.c_void_p)
+        # device_epoch: the kernels count the exchanges themselves (in the signal pad), so the
+        # launch arguments never change and a step can be replayed from a CUDA graph; otherwise
+        # the host passes 2 * call_index + 1
+        self.device_epoch = device_epoch
         self._calls = 0       # exchanges issued on these buffers (same on every rank)
         self._comms = [_Comm(self.rank, self.world, 1, addr(xp), addr(self._out_ptrs),
                              addr(self._resid_ptrs), addr(self._pads)) for xp in self._x_ptrs]
@@ -117,7 +122,7 @@ class FusedTPComm:
         """resid = (T)(sum over ranks of x[which]) + resid; returns out = rms_norm(resid) * weight
         (rows [:num_tokens]); identical on every rank."""
         from ._lib import check
-        self._comms[which].epoch = (2 * self._calls + 1) & 0xFFFFFFFF
+        self._comms[which].epoch = 0 if self.device_epoch else (2 * self._calls + 1) & 0xFFFFFFFF
         self._calls += 1
         check(self._norm(self._ct.byref(self._comms[which]), weight.data_ptr(), eps, num_tokens,
                          self.hidden, self._code, self._stream()))
@@ -126,7 +131,7 @@ class FusedTPComm:
     def allreduce(self, which: int, num_tokens: int) -> torch.Tensor:
         """out = sum over ranks of x[which] (rows [:num_tokens])."""
         from ._lib import check
-        self._comms[which].epoch = (2 * self._calls + 1) & 0xFFFFFFFF
+        self._comms[which].epoch = 0 if self.device_epoch else (2 * self._calls + 1) & 0xFFFFFFFF
         self._calls += 1
         check(self._plain(self._ct.byref(self._comms[which]), num_tokens, self.hidden, self._code,
                           self._stream()))

@@ -14,11 +14,17 @@
 // the row ONCE from HBM (2 or 4 bytes per logit) keeping an online (max, sum) pair and the running
 // arg-max of the sampling key, then counts the rank in a second sweep that hits L2.
 //
-// Random sampling uses the same exponential-race construction as the reference:
-//   argmax_i p_i / q_i,  q_i ~ Exp(1)   ==   argmax_i (x_i - log q_i)       (monotone transform)
-// The noise is either supplied by the caller (`noise` [R, V] fp32 exponential samples - what the
-// parity tests do, against the reference run on the same q) or drawn in the kernel from
-// Philox4x32-10 keyed by (seed, row, column): q = -log(u), u in (0, 1].
+// Random sampling, two forms with the same distribution:
+//   * caller-supplied noise (`noise` [R, V] fp32 Exp(1) samples): the reference's exponential
+//     race, argmax_i p_i / q_i == argmax_i (x_i - log q_i) - what the parity tests run, against
+//     the reference fed the same q;
+//   * no noise given (production): ONE uniform per row from Philox4x32-10 keyed by (seed, row,
+//     offset) and inversion of the row's cumulative distribution - per-thread partial sums from
+//     the sweep are scanned across the CTA, the thread whose range holds u * sum is found, and a
+//     warp resolves the position inside that thread's elements.  No per-element random numbers
+//     or logarithms: the sweep costs one exp per logit, like the greedy one.  (A race over V
+//     draws per row measured 4-5x slower than the memory sweep: Philox rounds and two MUFU
+//     logarithms per logit.)
 //
 // Bound: HBM, V*sizeof(T) bytes per row (+ 4*V when the caller supplies noise or asks for the
 // full probs / logprobs matrices).
@@ -106,6 +112,8 @@ __global__ void __launch_bounds__(kThreads)
   pdl_trigger();
 
   Acc a{-INFINITY, 0.f, -INFINITY, 0x7fffffff};
+  const bool race = rnd && nz != nullptr;      // exponential race over the caller's noise
+  const bool invert = rnd && nz == nullptr;    // inverse-CDF draw with one in-kernel uniform
   const bool vec_ok = (((uintptr_t)x) % 16 == 0);
   const int nvec = vec_ok ? vocab / N : 0;
   // ---- sweep 1: HBM -> (max, sum, arg-max of the key) ------------------------------------------
@@ -113,47 +121,23 @@ __global__ void __launch_bounds__(kThreads)
     Vec16<T> c;
     *reinterpret_cast<uint4*>(&c) = ld_nc_16(x + (int64_t)v * N);
     float q[N];
-    if (rnd) {
-      if (nz != nullptr) {
+    if (race) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) q[j] = nz[v * N + j];
-      } else {
-#pragma unroll
-        for (int j4 = 0; j4 < N; j4 += 4) {
-          const uint32_t ctr = (uint32_t)((v * N + j4) >> 2);
-          const uint4 r = philox4x32_10(make_uint4(ctr, (uint32_t)row, (uint32_t)offset,
-                                                   (uint32_t)(offset >> 32)), pkey);
-          q[j4] = -__logf(u01(r.x));
-          q[j4 + 1] = -__logf(u01(r.y));
-          q[j4 + 2] = -__logf(u01(r.z));
-          q[j4 + 3] = -__logf(u01(r.w));
-        }
-      }
+      for (int j = 0; j < N; ++j) q[j] = nz[v * N + j];
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const float f = scaled<T>(c.v[j], t, unit);
-      const float key = rnd ? (f == -INFINITY ? -INFINITY : f - __logf(q[j])) : f;
+      const float key = race ? (f == -INFINITY ? -INFINITY : f - __logf(q[j])) : f;
       acc_add(a, f, key, v * N + j);
     }
   }
   for (int i = nvec * N + threadIdx.x; i < vocab; i += kThreads) {   // tail / unaligned rows
     const float f = scaled<T>(x[i], t, unit);
-    float key = f;
-    if (rnd && f != -INFINITY) {
-      float q;
-      if (nz != nullptr) {
-        q = nz[i];
-      } else {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(i >> 2), (uint32_t)row, (uint32_t)offset,
-                                                 (uint32_t)(offset >> 32)), pkey);
-        const uint32_t w = (i & 3) == 0 ? r.x : ((i & 3) == 1 ? r.y : ((i & 3) == 2 ? r.z : r.w));
-        q = -__logf(u01(w));
-      }
-      key = f - __logf(q);
-    }
+    const float key = (race && f != -INFINITY) ? f - __logf(nz[i]) : f;
     acc_add(a, f, key, i);
   }
+  const float tm = a.m, ts = a.s;      // this thread's own (max, sum): the inversion needs them
   // the per-thread column order is increasing but threads interleave: merge with index tie-break
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
@@ -181,7 +165,130 @@ __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
   const Acc f = fin;
-  const int tok = f.idx < vocab ? f.idx : 0;
+  __shared__ float wtot[kThreads / 32];
+  __shared__ int sel_t;
+  __shared__ float sel_lt;
+  __shared__ int sel_tok;
+  if (invert) {
+    // inclusive scan over the threads of  S_t = sum over thread t's logits of exp(x - max)
+    const float st = tm == -INFINITY ? 0.f : ts * __expf(tm - f.m);
+    float incl = st;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (threadIdx.x == 0) sel_t = -1;
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    float total = 0.f, before = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      if (w < warp) before += wtot[w];
+      total += wtot[w];
+    }
+    // exclusive bound from the SAME sums as the neighbour's inclusive one: the threads' ranges
+    // tile [0, total] exactly, so exactly one of them holds the target
+    const float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    const float excl = before + (lane == 0 ? 0.f : prev);
+    incl += before;
+    const uint4 r4 = philox4x32_10(make_uint4((uint32_t)row, 0x5eedu, (uint32_t)offset,
+                                              (uint32_t)(offset >> 32)), pkey);
+    const float target = u01(r4.x) * total;           // in (0, total]
+    if (st > 0.f && excl < target && target <= incl) {
+      sel_t = threadIdx.x;
+      sel_lt = target - excl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int tstar = sel_t;
+      const float lt = sel_lt;
+      int chosen = -1, lastidx = -1;
+      float run = 0.f;
+      if (tstar >= 0) {
+        // the selected thread's elements in the order it summed them: vectors tstar + k*kThreads,
+        // then the scalar tail; lane k takes the k-th of them, 32 at a time
+        const int viters = nvec > tstar ? (nvec - tstar + kThreads - 1) / kThreads : 0;
+        for (int k0 = 0; k0 < viters && chosen < 0; k0 += 32) {
+          const int k = k0 + lane;
+          const bool ok = k < viters;
+          const int v = tstar + k * kThreads;
+          float e[N];
+          float part = 0.f;
+          int mylast = -1;
+          if (ok) {
+            Vec16<T> c;
+            *reinterpret_cast<uint4*>(&c) = *reinterpret_cast<const uint4*>(x + (int64_t)v * N);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              const float g = scaled<T>(c.v[j], t, unit);
+              e[j] = g == -INFINITY ? 0.f : __expf(g - f.m);
+              part += e[j];
+              if (e[j] > 0.f) mylast = v * N + j;
+            }
+          }
+          float inc = part;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+          }
+          const unsigned nzm = __ballot_sync(0xffffffffu, ok && part > 0.f);
+          const unsigned cross = __ballot_sync(0xffffffffu, ok && part > 0.f && run + inc >= lt);
+          if (cross != 0u) {
+            const int src = __ffs(cross) - 1;
+            int cand = -1;
+            if (lane == src) {
+              float r = run + inc - part;
+#pragma unroll
+              for (int j = 0; j < N; ++j) {
+                if (e[j] > 0.f && cand < 0) {
+                  r += e[j];
+                  if (r >= lt) cand = v * N + j;
+                }
+              }
+              if (cand < 0) cand = mylast;
+            }
+            chosen = __shfl_sync(0xffffffffu, cand, src);
+          } else if (nzm != 0u) {
+            lastidx = __shfl_sync(0xffffffffu, mylast, 31 - __clz(nzm));
+          }
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        const int t0 = nvec * N + tstar;
+        const int titers = vocab > t0 ? (vocab - t0 + kThreads - 1) / kThreads : 0;
+        for (int k0 = 0; k0 < titers && chosen < 0; k0 += 32) {
+          const int k = k0 + lane;
+          const bool ok = k < titers;
+          const int i = t0 + k * kThreads;
+          float part = 0.f;
+          if (ok) {
+            const float g = scaled<T>(x[i], t, unit);
+            part = g == -INFINITY ? 0.f : __expf(g - f.m);
+          }
+          float inc = part;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+          }
+          const unsigned nzm = __ballot_sync(0xffffffffu, ok && part > 0.f);
+          const unsigned cross = __ballot_sync(0xffffffffu, ok && part > 0.f && run + inc >= lt);
+          if (cross != 0u) {
+            chosen = t0 + (k0 + __ffs(cross) - 1) * kThreads;
+          } else if (nzm != 0u) {
+            lastidx = t0 + (k0 + 31 - __clz(nzm)) * kThreads;
+          }
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (chosen < 0) chosen = lastidx;      // partial sums rounded below the thread's total
+      }
+      if (lane == 0) sel_tok = chosen;
+    }
+    __syncthreads();
+  }
+  const int tok = invert ? (sel_tok >= 0 && sel_tok < vocab ? sel_tok : (f.idx < vocab ? f.idx : 0))
+                         : (f.idx < vocab ? f.idx : 0);
   const float lse = f.m + __logf(f.s);
   const float xc = scaled<T>(x[tok], t, unit);
 

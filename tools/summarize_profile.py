@@ -3,6 +3,7 @@
 
     python tools/summarize_profile.py launches gpurun_out/launches.csv profiles/r01_launches.md
     python tools/summarize_profile.py kernel   gpurun_out/attn_prof.ncu-rep profiles/r01_attention_ncu.md
+    python tools/summarize_profile.py kernel   gpurun_out/attn_prof.raw.csv profiles/r01_attention_ncu.md
 """
 import collections
 import csv
@@ -61,7 +62,10 @@ def launches(src, dst):
 
 
 def kernel(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if src.endswith(".csv"):      # already exported on the GPU box (tools/gpu_session.sh export_rep)
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:

@@ -117,19 +117,48 @@ __global__ void __launch_bounds__(kThreads)
   const bool vec_ok = (((uintptr_t)x) % 16 == 0);
   const int nvec = vec_ok ? vocab / N : 0;
   // ---- sweep 1: HBM -> (max, sum, arg-max of the key) ------------------------------------------
-  for (int v = threadIdx.x; v < nvec; v += kThreads) {
-    Vec16<T> c;
-    *reinterpret_cast<uint4*>(&c) = ld_nc_16(x + (int64_t)v * N);
-    float q[N];
-    if (race) {
+  // four 16-byte loads in flight per thread; per vector one rescale of the running sum (when the
+  // vector raises the maximum) and N independent exps - no per-element dependency chain
+  constexpr int U = 4;
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += U * kThreads) {
+    Vec16<T> c[U];
 #pragma unroll
-      for (int j = 0; j < N; ++j) q[j] = nz[v * N + j];
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kThreads;
+      if (v < nvec) *reinterpret_cast<uint4*>(&c[u]) = ld_nc_16(x + (int64_t)v * N);
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float f = scaled<T>(c.v[j], t, unit);
-      const float key = race ? (f == -INFINITY ? -INFINITY : f - __logf(q[j])) : f;
-      acc_add(a, f, key, v * N + j);
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kThreads;
+      if (v < nvec) {
+        float f[N];
+        float vm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          f[j] = scaled<T>(c[u].v[j], t, unit);
+          vm = fmaxf(vm, f[j]);
+        }
+        if (vm > a.m) {
+          a.s *= __expf(a.m - vm);          // a.m == -inf: a.s is 0 and stays 0
+          a.m = vm;
+        }
+        if (a.m != -INFINITY) {
+          float add = 0.f;
+#pragma unroll
+          for (int j = 0; j < N; ++j) add += __expf(f[j] - a.m);   // exp(-inf) == 0
+          a.s += add;
+        }
+        if (!invert) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            const float key = (race && f[j] != -INFINITY) ? f[j] - __logf(nz[v * N + j]) : f[j];
+            if (key > a.key) {     // columns arrive in increasing order: strict > keeps the first
+              a.key = key;
+              a.idx = v * N + j;
+            }
+          }
+        }
+      }
     }
   }
   for (int i = nvec * N + threadIdx.x; i < vocab; i += kThreads) {   // tail / unaligned rows
@@ -297,17 +326,28 @@ __global__ void __launch_bounds__(kThreads)
   const bool full = out_probs != nullptr || out_logprobs != nullptr;
   float* pr = out_probs != nullptr ? out_probs + (int64_t)row * vocab : nullptr;
   float* lp = out_logprobs != nullptr ? out_logprobs + (int64_t)row * vocab : nullptr;
-  for (int v = threadIdx.x; v < nvec; v += kThreads) {
-    Vec16<T> c;
-    *reinterpret_cast<uint4*>(&c) = *reinterpret_cast<const uint4*>(x + (int64_t)v * N);
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += U * kThreads) {
+    Vec16<T> c[U];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float g = scaled<T>(c.v[j], t, unit);
-      above += g > xc;
-      if (full) {
-        const float l = g - lse;
-        if (lp != nullptr) lp[v * N + j] = l;
-        if (pr != nullptr) pr[v * N + j] = __expf(l);
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kThreads;
+      if (v < nvec)
+        *reinterpret_cast<uint4*>(&c[u]) = *reinterpret_cast<const uint4*>(x + (int64_t)v * N);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float g = scaled<T>(c[u].v[j], t, unit);
+          above += g > xc;
+          if (full) {
+            const float l = g - lse;
+            if (lp != nullptr) lp[v * N + j] = l;
+            if (pr != nullptr) pr[v * N + j] = __expf(l);
+          }
+        }
       }
     }
   }

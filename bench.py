@@ -623,7 +623,10 @@ def _main(out):
         pass
     roofline = {"bound": "hbm", "kernel": "paged_attention (v1 entry; one launch: partitions of "
                 "long contexts are merged inside the kernel)", "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src,
+                "peak_note": "the measured peak is a COPY (half reads, half writes); a read-only "
+                             "stream like this kernel can run a few per cent above it",
+                "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
                 "launch_ms_mean": attn_b2b_ms,
                 "timed_in": f"{args.steps} x {shape.layers} consecutive launches (one per layer, "

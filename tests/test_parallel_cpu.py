@@ -3,6 +3,7 @@ and the vllm._C.custom_ar surface): integer-valued tensors so the sum must be ex
 reference's tests/distributed/test_custom_all_reduce.py:30-51."""
 import os
 import socket
+import sys
 
 import pytest
 import torch
@@ -54,13 +55,20 @@ def _worker(rank, world, port, q):
 
 
 def test_all_reduce_world2_gloo():
+    # spawned children re-import this module by name with the parent's sys.path: the repo root
+    # must come before /root/reference (which other tests put first and which has its own
+    # `tests` package)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root in sys.path:
+        sys.path.remove(root)
+    sys.path.insert(0, root)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res

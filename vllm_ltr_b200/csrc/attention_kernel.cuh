@@ -519,7 +519,7 @@ __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p,
 
 // ---- the kernel ----------------------------------------------------------------------------------
 template <typename T, typename CT, int D, int BS, int GT, bool MMA>
-__global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_constant__ Params p) {
   using C = Cfg<T, CT, D, BS, GT, MMA>;
   using QS = typename C::QS;
   using MT = typename C::MT;
@@ -739,25 +739,36 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
     }
 
     // running softmax state.  FMA: per head, replicated over the lanes of a token / row.
-    // MMA: rows g (and g+8) of the 16-row tile, replicated over the 4 lanes of a row.
-    constexpr int NR = MMA ? (C::R16 ? 2 : 1) : GT;
+    // MMA: both products are computed TRANSPOSED, so that the 16-row M dimension of
+    // mma.m16n8k16 is always full and the 8-wide N dimension carries the query heads:
+    //   S^T[token, head] = K[token, :] . Q^T[:, head]     A = K tile rows,  B = q fragments
+    //   O^T[d, head]    += V^T[d, token] . P^T[token, head]   A = V tile rows,  B = P^T
+    // (the head-major orientation pads 8 heads to 16 rows: twice the mma count, zero operand
+    // registers to shuffle, and 64 instead of 32 accumulator registers for O).  A thread owns
+    // head columns 8nh + 2t4 + {0,1} (replicated over the 8 row groups g): HC of them.
+    constexpr int NH = MMA ? GT / 8 : 1;              // 8-head N tiles
+    constexpr int HC = 2 * NH;                        // head columns per thread
+    constexpr int MTL = MMA ? (BS + 15) / 16 : 1;     // 16-token M tiles per KV block
+    constexpr int DT = D / 16;                        // 16-row tiles of the head dimension
+    constexpr int NR = MMA ? HC : GT;
     float m[NR], l[NR], slope[NR];
     float acc[MMA ? 1 : GT][MMA ? 1 : C::RI];
-    float o_acc[MMA ? C::ND : 1][4];
+    float o_acc[MMA ? DT * NH : 1][4];   // [dt][nh]: (d = 16dt+g, heads 2t4,2t4+1), (d + 8, same heads)
     uint32_t qa[MMA ? C::KS : 1][4];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       m[r] = -INFINITY;
       l[r] = 0.f;
-      const int h = MMA ? g + 8 * r : r;
+      const int h = MMA ? 8 * (r >> 1) + 2 * t4 + (r & 1) : r;
       slope[r] = (p.alibi_slopes != nullptr && h < nheads) ? p.alibi_slopes[head0 + h] * kLog2e : 0.f;
     }
     if constexpr (MMA) {
 #pragma unroll
-      for (int i = 0; i < C::ND; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
-      // q fragments (A operand, 16 rows = query heads, k = head dim).  For e5m2 caches the k
-      // slots of a step are permuted so that a thread's four K bytes are contiguous:
-      // slots {2t,2t+1,2t+8,2t+9} <-> head-dim offsets {4t,4t+1,4t+2,4t+3}.
+      for (int i = 0; i < DT * NH; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+      // q fragments: B operand of S^T = K . Q^T; for head tile nh the pair (qa[ks][nh],
+      // qa[ks][2 + nh]) holds Q[head 8nh + g][k slots 2t4,2t4+1 | 2t4+8,2t4+9] of k-step ks.  For
+      // e5m2 caches the k slots of a step are permuted so that a thread's four K bytes are
+      // contiguous: slots {2t,2t+1,2t+8,2t+9} <-> head-dim offsets {4t,4t+1,4t+2,4t+3}.
       const T* qg = reinterpret_cast<const T*>(p.q) + (int64_t)seq * p.q_stride + (int64_t)head0 * D;
 #pragma unroll
       for (int ks = 0; ks < C::KS; ++ks) {
@@ -782,8 +793,8 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
               hi = *reinterpret_cast<const uint32_t*>(src + 8 + 2 * t4);
             }
           }
-          qa[ks][r] = lo;        // a0 (row g) / a1 (row g+8): k slots 2t, 2t+1
-          qa[ks][2 + r] = hi;    // a2 / a3: k slots 2t+8, 2t+9
+          qa[ks][r] = lo;        // b0 of head tile r: k slots 2t, 2t+1
+          qa[ks][2 + r] = hi;    // b1 of head tile r: k slots 2t+8, 2t+9
         }
       }
     } else {
@@ -840,130 +851,147 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
         }
-        float s[C::NT][4];
+        const int j = lane >> 3;      // ldmatrix: lane supplies row (lane & 7) of matrix j
+        float st[MTL][NH][4];         // S^T: (token g | g+8 of M tile mt, heads 2t4,2t4+1 of tile nh)
 #pragma unroll
-        for (int nt = 0; nt < C::NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        if constexpr (!C::FP8) {
-          // K tile [D/8][BS][8]: chunk c, tokens 8nt..8nt+7 is one 8x8 b16 matrix (rows 16 B apart)
+        for (int mt = 0; mt < MTL; ++mt)
 #pragma unroll
-          for (int ks = 0; ks < C::KS; ++ks) {
-            if constexpr (C::NT >= 2) {
+          for (int nh = 0; nh < NH; ++nh) st[mt][nh][0] = st[mt][nh][1] = st[mt][nh][2] = st[mt][nh][3] = 0.f;
 #pragma unroll
-              for (int np = 0; np < C::NT / 2; ++np) {
-                uint32_t b[4];
-                const int j = lane >> 3;
-                ldsm_x4(ktile + (((2 * ks + (j & 1)) * BS + 16 * np + 8 * (j >> 1) + (lane & 7)) << 4), b);
-                mma16816<MT>(s[2 * np], qa[ks], b[0], b[1]);
-                mma16816<MT>(s[2 * np + 1], qa[ks], b[2], b[3]);
+        for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+          for (int mt = 0; mt < MTL; ++mt) {
+            uint32_t a[4];
+            if constexpr (!C::FP8) {
+              // K tile [D/8][BS][8]: (chunk c, tokens 8b..8b+7) is one 8x8 b16 matrix, rows 16 B
+              // apart.  A fragment: a0 = (tokens 0-7, k 0-7), a1 = (tokens 8-15, k 0-7),
+              // a2 = (tokens 0-7, k 8-15), a3 = (tokens 8-15, k 8-15)
+              if constexpr (BS >= 16) {
+                ldsm_x4(ktile + (((2 * ks + (j >> 1)) * BS + 16 * mt + 8 * (j & 1) + (lane & 7)) << 4), a);
+              } else {   // BS == 8: tokens 8..15 of the M tile do not exist
+                ldsm_x4(ktile + (((2 * ks + (j >> 1)) * BS + (lane & 7)) << 4), a);
+                a[1] = 0u;
+                a[3] = 0u;
               }
-            } else {   // BS == 8: one n-tile; matrices 2,3 of the x4 load are ignored duplicates
-              uint32_t b[4];
-              const int j = (lane >> 3) & 1;
-              ldsm_x4(ktile + (((2 * ks + j) * BS + (lane & 7)) << 4), b);
-              mma16816<MT>(s[0], qa[ks], b[0], b[1]);
+            } else {
+              // e5m2 K tile [D/16][BS][16]: bytes 4t4..4t4+3 of (k-step ks, token) are this
+              // thread's four k slots
+              const uint32_t w0 = lds4(ktile + ((ks * BS + 16 * mt + g) << 4) + 4 * t4);
+              a[0] = __byte_perm(w0, 0, 0x1404);
+              a[2] = __byte_perm(w0, 0, 0x3424);
+              if constexpr (BS >= 16) {
+                const uint32_t w1 = lds4(ktile + ((ks * BS + 16 * mt + 8 + g) << 4) + 4 * t4);
+                a[1] = __byte_perm(w1, 0, 0x1404);
+                a[3] = __byte_perm(w1, 0, 0x3424);
+              } else {
+                a[1] = 0u;
+                a[3] = 0u;
+              }
             }
-          }
-        } else {
-          // e5m2 K tile [D/16][BS][16]: thread (g, t4) reads bytes 4t4..4t4+3 of token n = 8nt+g
 #pragma unroll
-          for (int ks = 0; ks < C::KS; ++ks) {
-#pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
-              const uint32_t w = lds4(ktile + ((ks * BS + 8 * nt + g) << 4) + 4 * t4);
-              mma16816<MT>(s[nt], qa[ks], __byte_perm(w, 0, 0x1404), __byte_perm(w, 0, 0x3424));
-            }
+            for (int nh = 0; nh < NH; ++nh) mma16816<MT>(st[mt][nh], a, qa[ks][nh], qa[ks][2 + nh]);
           }
         }
-        // ---- online softmax on the fragments (log2 domain) --------------------------------------
-        uint32_t pa[C::KT][4];
-#pragma unroll
-        for (int kt = 0; kt < C::KT; ++kt) pa[kt][0] = pa[kt][1] = pa[kt][2] = pa[kt][3] = 0u;
+        // ---- online softmax down the token rows of each head column (log2 domain) --------------
         // only the context's last block can hold out-of-context tokens, and ALiBi is rare: the
         // common tile takes the short form (bit-identical: slope == 0 adds +0)
-        const bool plain = !last_partial && p.alibi_slopes == nullptr;
+        const bool plain = !last_partial && p.alibi_slopes == nullptr && BS >= 16;
+        uint32_t pb[MTL][NH][2];      // P^T as B operand: [0] tokens 2t4,2t4+1; [1] tokens 8+2t4,9+2t4
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          float mx = -INFINITY;
-          if (plain) {
+        for (int nh = 0; nh < NH; ++nh) {
+          float m_new[2];
 #pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * nh + e;
+            float mx = -INFINITY;
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float sv = s[nt][2 * r + e] * scale_l2;
-                s[nt][2 * r + e] = sv;
+            for (int mt = 0; mt < MTL; ++mt) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float sv = st[mt][nh][2 * hh + e] * scale_l2;
+                if (!plain) {
+                  const int row = 16 * mt + 8 * hh + g;
+                  const int tok = tok0 + row;
+                  sv += slope[c] * (float)(tok - ctx + 1);
+                  sv = (tok < ctx && row < BS) ? sv : -INFINITY;
+                }
+                st[mt][nh][2 * hh + e] = sv;
                 mx = fmaxf(mx, sv);
               }
             }
-          } else {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            m_new[e] = fmaxf(m[c], mx);     // finite: a scheduled tile has a valid token
+            // the running maximum settles after the first tiles: rescale only when some head's
+            // maximum moved (warp-uniform; alpha == 1 exactly otherwise)
+            if (__any_sync(0xffffffffu, m_new[e] != m[c])) {
+              const float alpha = exp2f(m[c] - m_new[e]);
+              m[c] = m_new[e];
+              l[c] *= alpha;
 #pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int tok = tok0 + 8 * nt + 2 * t4 + e;
-                float sv = s[nt][2 * r + e] * scale_l2 + slope[r] * (float)(tok - ctx + 1);
-                sv = tok < ctx ? sv : -INFINITY;
-                s[nt][2 * r + e] = sv;
-                mx = fmaxf(mx, sv);
+              for (int dt = 0; dt < DT; ++dt) {
+                o_acc[dt * NH + nh][e] *= alpha;
+                o_acc[dt * NH + nh][2 + e] *= alpha;
               }
             }
           }
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          const float m_new = fmaxf(m[r], mx);    // finite: a scheduled tile has a valid token
-          // the running maximum settles after the first tiles: rescale only when some row's
-          // maximum moved (warp-uniform; alpha == 1 exactly otherwise)
-          if (__any_sync(0xffffffffu, m_new != m[r])) {
-            const float alpha = exp2f(m[r] - m_new);
-            m[r] = m_new;
-            l[r] *= alpha;
 #pragma unroll
-            for (int i = 0; i < C::ND; ++i) {
-              o_acc[i][2 * r] *= alpha;
-              o_acc[i][2 * r + 1] *= alpha;
+          for (int mt = 0; mt < MTL; ++mt) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              if (BS >= 16 || hh == 0) {
+                // (token row, heads 2t4 and 2t4+1) packed, rounded to the operand type; the row
+                // sums use the rounded weights, like the products do
+                const uint32_t pk = pack2<MT>(exp2f(st[mt][nh][2 * hh] - m_new[0]),
+                                              exp2f(st[mt][nh][2 * hh + 1] - m_new[1]));
+                const float2 pf = unpack2<MT>(pk);
+                l[2 * nh] += pf.x;
+                l[2 * nh + 1] += pf.y;
+                // 8x8 transpose across the warp: (token g, heads 2t4..) -> (head g, tokens 2t4..)
+                uint32_t tr_;
+                asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(tr_) : "r"(pk));
+                pb[mt][nh][hh] = tr_;
+              } else {
+                pb[mt][nh][hh] = 0u;
+              }
             }
-          }
-#pragma unroll
-          for (int nt = 0; nt < C::NT; ++nt) {
-            const uint32_t pk = pack2<MT>(exp2f(s[nt][2 * r] - m_new), exp2f(s[nt][2 * r + 1] - m_new));
-            const float2 pf = unpack2<MT>(pk);
-            l[r] += pf.x + pf.y;                   // the sum uses the rounded p, like the weights
-            pa[nt >> 1][(nt & 1) * 2 + r] = pk;    // a0/a1: tokens 16kt+2t.. ; a2/a3: +8
           }
         }
-        // ---- o += p.v ---------------------------------------------------------------------------
-        if constexpr (!C::FP8) {
-          // V tile [D][BS]: rows 8nd..8nd+7, tokens 16kt+8h..+7 is one 8x8 matrix (rows 2*BS B apart)
+        // ---- O^T += V^T . P^T -------------------------------------------------------------------
 #pragma unroll
-          for (int kt = 0; kt < C::KT; ++kt) {
+        for (int mt = 0; mt < MTL; ++mt) {
 #pragma unroll
-            for (int nd = 0; nd < C::ND; nd += 2) {
-              uint32_t b[4];
-              const int j = lane >> 3;
+          for (int dt = 0; dt < DT; ++dt) {
+            uint32_t a[4];
+            if constexpr (!C::FP8) {
+              // V tile [D][BS]: (rows 8b..8b+7, tokens 8c..8c+7) is one 8x8 matrix, rows 2*BS B
+              // apart.  a0 = (d 0-7, tok 0-7), a1 = (d 8-15, tok 0-7), a2 = (d 0-7, tok 8-15), a3
               if constexpr (BS >= 16) {
-                ldsm_x4(vtile + ((8 * (nd + (j >> 1)) + (lane & 7)) * BS + 16 * kt + 8 * (j & 1)) * 2, b);
-                mma16816<MT>(o_acc[nd], pa[kt], b[0], b[1]);
-                mma16816<MT>(o_acc[nd + 1], pa[kt], b[2], b[3]);
-              } else {   // BS == 8: tokens 8..15 of the k-step do not exist (p = 0 there)
-                ldsm_x4(vtile + ((8 * (nd + (j >> 1)) + (lane & 7)) * BS) * 2, b);
-                mma16816<MT>(o_acc[nd], pa[kt], b[0], 0u);
-                mma16816<MT>(o_acc[nd + 1], pa[kt], b[2], 0u);
+                ldsm_x4(vtile + ((16 * dt + 8 * (j & 1) + (lane & 7)) * BS + 16 * mt + 8 * (j >> 1)) * 2, a);
+              } else {
+                ldsm_x4(vtile + ((16 * dt + 8 * (j & 1) + (lane & 7)) * BS) * 2, a);
+                a[2] = 0u;
+                a[3] = 0u;
               }
+            } else {
+              // e5m2 V tile [D][BS] bytes: two 16-bit loads per (row, half of the token step)
+              const uint32_t row0 = vtile + (16 * dt + g) * BS + 16 * mt + 2 * t4;
+              uint32_t w0, w1, w2 = 0, w3 = 0;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w0) : "r"(row0));
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w1) : "r"(row0 + 8 * BS));
+              if constexpr (BS >= 16) {
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w2) : "r"(row0 + 8));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w3) : "r"(row0 + 8 * BS + 8));
+              }
+              a[0] = __byte_perm(w0, 0, 0x1404);
+              a[1] = __byte_perm(w1, 0, 0x1404);
+              a[2] = __byte_perm(w2, 0, 0x1404);
+              a[3] = __byte_perm(w3, 0, 0x1404);
             }
-          }
-        } else {
-          // e5m2 V tile [D][BS] bytes.  p's k slots are tokens 16kt + {2t,2t+1,8+2t,9+2t}: two
-          // 16-bit loads per (row, k-step)
 #pragma unroll
-          for (int kt = 0; kt < C::KT; ++kt) {
-#pragma unroll
-            for (int nd = 0; nd < C::ND; ++nd) {
-              const uint32_t row = vtile + (8 * nd + g) * BS + 16 * kt;
-              uint32_t w0, w1 = 0;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w0) : "r"(row + 2 * t4));
-              if constexpr (BS >= 16)
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w1) : "r"(row + 8 + 2 * t4));
-              mma16816<MT>(o_acc[nd], pa[kt], __byte_perm(w0, 0, 0x1404), __byte_perm(w1, 0, 0x1404));
-            }
+            for (int nh = 0; nh < NH; ++nh)
+              mma16816<MT>(o_acc[dt * NH + nh], a, pb[mt][nh][0], pb[mt][nh][1]);
           }
         }
       } else {
@@ -1064,10 +1092,12 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
     // Layout-independent description of what this lane owns: FMA: head h, rows v_row + i*RPI
     // (lanes v_sub == 0); MMA: rows g (+8), columns 8nd + 2t4 + {0,1}.
     if constexpr (MMA) {
+      // every row group g holds partial row sums of its own tokens
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
-        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 4);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 8);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 16);
       }
     } else {
 #pragma unroll
@@ -1087,30 +1117,33 @@ __global__ void __launch_bounds__(128, MMA ? 3 : 1) paged_attention_kernel(const
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const int h = MMA ? g + 8 * r : r;
+      const int h = MMA ? 8 * (r >> 1) + 2 * t4 + (r & 1) : r;
       if (h < nheads) {
         const int head = head0 + h;
         const float inv = __fdividef(1.f, l[r] + 1e-6f);
         const int64_t pi = ((int64_t)seq * p.num_heads + head) * p.n_part + part;
-        if (partial && (MMA ? t4 == 0 : lane == 0)) {
+        if (partial && (MMA ? g == 0 : lane == 0)) {
           p.max_logits[pi] = m[r] * kLn2;  // natural-log domain, as the reference stores qk_max
           p.exp_sums[pi] = l[r];
         }
         T* o = reinterpret_cast<T*>(p.out) + ((int64_t)seq * p.num_heads + head) * D;
         const bool direct = cur.nparts == 1;   // single partition: the result is final
         if constexpr (MMA) {
+          // this thread's column of O^T: rows d = 16dt + g and 16dt + g + 8 (the 8 row groups of
+          // a head column write 8 consecutive elements)
 #pragma unroll
-          for (int nd = 0; nd < C::ND; ++nd) {
-            const int col = 8 * nd + 2 * t4;
-            const float v0 = o_acc[nd][2 * r] * inv, v1 = o_acc[nd][2 * r + 1] * inv;
-            if (direct) *reinterpret_cast<uint32_t*>(o + col) = pack2<T>(v0, v1);
-            if (partial) {
-              if (p.tmp_is_f32)
-                *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.tmp_out) + pi * D + col) =
-                    make_float2(v0, v1);
-              else
-                *reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.tmp_out) + pi * D + col) =
-                    pack2<T>(v0, v1);
+          for (int dt = 0; dt < DT; ++dt) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int d = 16 * dt + 8 * hh + g;
+              const float v = o_acc[dt * NH + (r >> 1)][2 * hh + (r & 1)] * inv;
+              if (direct) o[d] = ST<T>::from_f(v);
+              if (partial) {
+                if (p.tmp_is_f32)
+                  reinterpret_cast<float*>(p.tmp_out)[pi * D + d] = v;
+                else
+                  reinterpret_cast<T*>(p.tmp_out)[pi * D + d] = ST<T>::from_f(v);
+              }
             }
           }
         } else if (v_sub == 0) {

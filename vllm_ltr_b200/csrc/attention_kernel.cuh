@@ -21,10 +21,12 @@
 //   3 __syncthreads + smem tree per CTA         in the main loop (warps are independent)
 //   q.k with cvt f16->f32 + FFMA; p.v in        G == 1: FHFMA (fma.rn.f32.f16/.bf16, sm_100
 //   half precision (mul.f16x2)                  mixed-precision FMA), fp32 accumulation.
-//                                               G >= 2: the G query heads of a kv head form the
-//                                               M rows of mma.sync.m16n8k16 (K / V fragments by
-//                                               ldmatrix straight from the paged tile layout),
-//                                               so a KV byte costs ~10x fewer instructions
+//                                               G >= 2: tensor cores, both products transposed
+//                                               (S^T = K.Q^T, O^T = V^T.P^T): tokens / head-dim
+//                                               rows fill the 16-row M of mma.sync.m16n8k16, the
+//                                               query heads of the kv head ride its 8-wide N; K / V
+//                                               fragments by ldmatrix straight from the paged tile
+//                                               layout, P^T by movmatrix from the S^T accumulators
 //   static grid; v2 = second kernel that        persistent grid; contexts are cut into
 //   merges 512-token partitions through         partitions sized to fill the machine, a seq's
 //   global memory                               partitions are merged by whichever warp finishes

@@ -124,6 +124,17 @@ int vltr_copy_blocks(void* const* key_cache_ptrs, void* const* value_cache_ptrs,
  * memory takes one cudaMemcpyAsync per run of consecutive blocks. */
 int vltr_swap_blocks(const void* src, void* dst, int kind, const int64_t* block_mapping,
                      int num_pairs, int64_t block_bytes, void* stream);
+/* One swap of ALL layers in one launch (next row).  CacheEngine.swap_in /
+ * swap_out (vllm/worker/cache_engine.py:92-100) call PagedAttention.swap_blocks
+ * (vllm/attention/ops/paged_attn.py:195-206) per layer, i.e. swap_blocks 2 x layers times, and the
+ * reference issues one cudaMemcpyAsync per block in each (csrc/cache_kernels.cu:50-61).
+ * src_ptrs / dst_ptrs: HOST arrays of num_bufs buffer pointers (the K and the V cache of every
+ * layer, each [num_blocks, block_bytes]); kind as in vltr_swap_blocks; the same block_mapping
+ * applies to every buffer.  Pinned host buffers are gathered / scattered by one kernel over UVA;
+ * pageable ones fall back to vltr_swap_blocks per buffer. */
+int vltr_swap_blocks_layers(const void* const* src_ptrs, void* const* dst_ptrs, int num_bufs,
+                            int kind, const int64_t* block_mapping, int num_pairs,
+                            int64_t block_bytes, void* stream);
 
 /* convert_fp8 (:298-339): numel elements; exactly one of src/dst dtype is VLTR_U8. */
 int vltr_convert_fp8(const void* src, void* dst, int64_t numel, int src_dtype, int dst_dtype,

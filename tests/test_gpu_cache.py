@@ -161,6 +161,46 @@ def test_swap_blocks(cache_ops, direction, head_size, block_size, dtype, kv, pin
     assert torch.equal(dv[0].cpu(), ev)
 
 
+@pytest.mark.parametrize("direction", [("cuda", "cpu"), ("cpu", "cuda"), ("cuda", "cuda")])
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("kv", ["auto", "fp8"])
+def test_swap_blocks_layers(cache_ops, direction, pinned, kv):
+    """All layers of CacheEngine.swap_in / swap_out in one call (cache_engine.py:92-100) against
+    the reference loop: per layer, swap_blocks on the K half and on the V half
+    (paged_attn.py:195-206)."""
+    if "cpu" not in direction and not pinned:
+        pytest.skip("pinning only matters for host memory")
+    rnd = random.Random(1)
+    layers, nb, n, bs, hkv, D = 5, 128, 48, 16, 4, 64
+    dtype = torch.uint8 if kv == "fp8" else torch.half
+    g = torch.Generator().manual_seed(3)
+
+    def make(dev, seed_off):
+        out = []
+        for _ in range(layers):
+            t = torch.randint(0, 255, (2, nb, bs * hkv * D), generator=g, dtype=torch.uint8)
+            t = t if dtype == torch.uint8 else t.to(torch.int16).view(torch.half).clone()
+            t = t.to(DEV) if dev == "cuda" else (t.pin_memory() if pinned else t)
+            out.append(t)
+        return out
+
+    src, dst = make(direction[0], 0), make(direction[1], 1)
+    src_blocks = rnd.sample(range(nb), n)
+    dst_blocks = rnd.sample(range(nb), n)
+    if direction == ("cuda", "cuda"):
+        dst = src
+        dst_blocks = rnd.sample(list(set(range(nb)) - set(src_blocks)), n)
+    mapping = dict(zip(src_blocks, dst_blocks))
+    want = [d.cpu().clone() for d in dst]
+    for s, w in zip(src, want):
+        K.swap_blocks(s[0].cpu(), w[0], mapping)
+        K.swap_blocks(s[1].cpu(), w[1], mapping)
+    cache_ops.swap_blocks_layers(src, dst, mapping)
+    torch.cuda.synchronize()
+    for d, w in zip(dst, want):
+        assert torch.equal(d.cpu().view(torch.uint8), w.view(torch.uint8))
+
+
 def test_swap_blocks_errors(cache_ops):
     a = torch.zeros(4, 8, dtype=torch.half)
     with pytest.raises(RuntimeError, match="Invalid device combination"):

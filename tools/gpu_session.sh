@@ -33,6 +33,8 @@ for s in $STEPS; do
     ncumma)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 3 -c 1 -f -o $OUT/attn_mma_prof python tools/op_sweep.py --ops attn --only 8b-gqa-bf16:256:trace:v1 > $OUT/ncumma.log 2>&1; echo "ncumma rc=$?"; tail -3 $OUT/ncumma.log
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 3 -c 1 -f -o $OUT/attn_tp8_prof python tools/op_sweep.py --ops attn --only 70b-tp8-bf16:256:512:v1 > $OUT/ncutp8.log 2>&1; echo "ncutp8 rc=$?"; tail -3 $OUT/ncutp8.log ;;
     sweepsampler) timeout 600 python tools/op_sweep.py --ops sampler --json $OUT/sweep_sampler.json > $OUT/sweep_sampler.log 2>&1; echo "sweepsampler rc=$?"; cat $OUT/sweep_sampler.log ;;
+    swaptest) timeout 300 python -m pytest tests/test_gpu_cache.py -q -k "swap" -p no:cacheprovider > $OUT/swaptest.log 2>&1; echo "swaptest rc=$?"; tail -6 $OUT/swaptest.log
+              timeout 300 python tools/op_sweep.py --ops swap > $OUT/sweep_swap.log 2>&1; echo "sweepswap rc=$?"; cat $OUT/sweep_swap.log ;;
     sweepsmall) timeout 600 python tools/op_sweep.py --ops rms,silu,rope,cache --json $OUT/sweep_small.json > $OUT/sweep_small.log 2>&1; echo "sweepsmall rc=$?"; cat $OUT/sweep_small.log ;;
     sweeppred) timeout 600 python tools/op_sweep.py --ops gemm,predictor --json $OUT/sweep_pred.json > $OUT/sweep_pred.log 2>&1; echo "sweeppred rc=$?"; cat $OUT/sweep_pred.log ;;
     ncugemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 20 -c 3 -f -o $OUT/gemm_prof python tools/op_sweep.py --ops gemm > $OUT/ncugemm.log 2>&1; echo "ncugemm rc=$?"; tail -3 $OUT/ncugemm.log ;;

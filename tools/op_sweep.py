@@ -214,6 +214,42 @@ def main():
         ours = timeit(lambda: _C.cache_ops.copy_blocks(ks, vs, mapping), iters=10)
         rr = timeit(lambda: ref.cache_ops.copy_blocks(ks, vs, mapping), iters=10) if ref else None
         report("copy_blocks", "32 layers x 64 pairs x 128 KiB", byts, ours, rr)
+    if "swap" in ops_sel:
+        # one preemption-sized swap-out: 32 layers x 64 blocks (7B block: 128 KiB per K and V) to
+        # pinned host memory; ours = one launch for all layers, reference = its loop of
+        # swap_blocks per layer and K/V (one cudaMemcpyAsync per block inside)
+        L, nb, npairs = 32, 512, 64
+        gpu = [torch.zeros(2, nb, 16 * 32 * 128, dtype=torch.bfloat16, device=DEV) for _ in range(L)]
+        cpu = [torch.zeros(2, nb, 16 * 32 * 128, dtype=torch.bfloat16).pin_memory() for _ in range(L)]
+        mapping = {i * 3: i for i in range(npairs)}
+        byts = L * 2 * npairs * (16 * 32 * 128 * 2)
+
+        def ref_loop():
+            for i in range(L):
+                ref.cache_ops.swap_blocks(gpu[i][0], cpu[i][0], mapping)
+                ref.cache_ops.swap_blocks(gpu[i][1], cpu[i][1], mapping)
+
+        def ours_loop():
+            for i in range(L):
+                _C.cache_ops.swap_blocks(gpu[i][0], cpu[i][0], mapping)
+                _C.cache_ops.swap_blocks(gpu[i][1], cpu[i][1], mapping)
+        import time as _t
+        for name, fn in (("ours, one launch", lambda: _C.cache_ops.swap_blocks_layers(gpu, cpu, mapping)),
+                         ("ours, per layer", ours_loop), ("reference loop", ref_loop if ref else None)):
+            if fn is None:
+                continue
+            fn()
+            torch.cuda.synchronize()
+            t0 = _t.perf_counter()
+            for _ in range(5):
+                fn()
+            t1 = _t.perf_counter()
+            torch.cuda.synchronize()
+            t2 = _t.perf_counter()
+            print(f"swap_out   32 layers x 64 blocks x 128 KiB (K+V) = {byts/1e6:.0f} MB  {name:18s} "
+                  f"host issue {(t1-t0)/5*1e3:7.2f} ms  end to end {(t2-t0)/5*1e3:7.2f} ms  "
+                  f"{byts*5/(t2-t0)/1e9:6.1f} GB/s", flush=True)
+            rows.append(dict(op="swap_out", shape=name, ms=(t2 - t0) / 5 * 1e3))
     if "sampler" in ops_sel:
         # next-token sampling: ours (one kernel) next to the reference's tensor program
         # (sampler.py:67-80, :333-357, :528-544) written with the same torch calls

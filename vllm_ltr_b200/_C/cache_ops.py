@@ -35,6 +35,50 @@ def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping: Dict[int, i
                                    len(flat) // 2, block_bytes, stream_of(dev_t)))
 
 
+def swap_blocks_layers(src_kv_caches: List[torch.Tensor], dst_kv_caches: List[torch.Tensor],
+                       block_mapping: Dict[int, int]) -> None:
+    """Every layer of CacheEngine.swap_in / swap_out (vllm/worker/cache_engine.py:92-100) in one
+    call: ``*_kv_caches[i]`` is layer i's ``[2, num_blocks, ...]`` cache on the GPU or in (pinned)
+    host memory; the reference loops ``PagedAttention.swap_blocks`` over the layers
+    (paged_attn.py:195-206).  Not part of the reference's ``vllm._C`` surface."""
+    if len(src_kv_caches) != len(dst_kv_caches):
+        raise RuntimeError("src and dst must have the same number of layers")
+    if not src_kv_caches:
+        return
+    s0, d0 = src_kv_caches[0], dst_kv_caches[0]
+    if s0.is_cuda and d0.is_cuda:
+        kind, dev_t = 0, s0
+    elif s0.is_cuda and d0.device.type == "cpu":
+        kind, dev_t = 1, s0
+    elif s0.device.type == "cpu" and d0.is_cuda:
+        kind, dev_t = 2, d0
+    else:
+        raise RuntimeError("Invalid device combination")
+    bufs_s, bufs_d = [], []
+    for s, d in zip(src_kv_caches, dst_kv_caches):
+        if s.device != s0.device or d.device != d0.device or s.shape[0] != 2 or d.shape[0] != 2:
+            raise RuntimeError("every layer must be a [2, num_blocks, ...] cache on the same devices")
+        bufs_s += [s[0].data_ptr(), s[1].data_ptr()]
+        bufs_d += [d[0].data_ptr(), d[1].data_ptr()]
+    block_bytes = s0.element_size() * s0[0][0].numel()
+    flat: List[int] = []
+    for s, d in sorted(block_mapping.items()):
+        flat.append(s)
+        flat.append(d)
+    n = len(bufs_s)
+    with device_of(dev_t):
+        check(lib.vltr_swap_blocks_layers((ctypes.c_void_p * n)(*bufs_s), (ctypes.c_void_p * n)(*bufs_d),
+                                          n, kind, _pairs(flat), len(flat) // 2, block_bytes,
+                                          stream_of(dev_t)))
+
+
+def install_cache_engine(cache_engine) -> None:
+    """Re-bind ``swap_in`` / ``swap_out`` of a reference ``CacheEngine``
+    (vllm/worker/cache_engine.py:92-100) to the one-launch form."""
+    cache_engine.swap_in = lambda m: swap_blocks_layers(cache_engine.cpu_cache, cache_engine.gpu_cache, m)
+    cache_engine.swap_out = lambda m: swap_blocks_layers(cache_engine.gpu_cache, cache_engine.cpu_cache, m)
+
+
 def copy_blocks(key_caches: List[torch.Tensor], value_caches: List[torch.Tensor],
                 block_mapping: Dict[int, List[int]]) -> None:
     """csrc/cache_kernels.cu:97-152."""

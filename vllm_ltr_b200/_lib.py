@@ -33,6 +33,7 @@ _SIGS = {
                                        c_int64, c_int64, c_int, c_int, c_float, _P]),
     "vltr_copy_blocks": (c_int, [_P, _P, c_int, _P, c_int, c_int64, _P]),
     "vltr_swap_blocks": (c_int, [_P, _P, c_int, _P, c_int, c_int64, _P]),
+    "vltr_swap_blocks_layers": (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int64, _P]),
     "vltr_convert_fp8": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
     "vltr_rms_norm": (c_int, [_P, _P, _P, c_float, c_int, c_int, c_int, _P]),
     "vltr_fused_add_rms_norm": (c_int, [_P, _P, _P, c_float, c_int, c_int, c_int, _P]),

@@ -313,6 +313,47 @@ extern "C" int vltr_swap_blocks(const void* src, void* dst, int kind,
   return VLTR_OK;
 }
 
+extern "C" int vltr_swap_blocks_layers(const void* const* src_ptrs, void* const* dst_ptrs,
+                                       int num_bufs, int kind, const int64_t* block_mapping,
+                                       int num_pairs, int64_t block_bytes, void* stream) {
+  using namespace vltr;
+  VLTR_CHECK(kind >= 0 && kind <= 2, VLTR_ERR_INVALID, "swap_blocks: Invalid device combination");
+  VLTR_CHECK(num_bufs >= 0 && num_pairs >= 0 && block_bytes >= 0, VLTR_ERR_INVALID,
+             "swap_blocks: negative size");
+  if (num_bufs == 0 || num_pairs == 0 || block_bytes == 0) return VLTR_OK;
+  const char** src = (const char**)alloca(sizeof(char*) * num_bufs);
+  char** dst = (char**)alloca(sizeof(char*) * num_bufs);
+  bool mapped = true;
+  for (int i = 0; i < num_bufs && mapped; ++i) {
+    src[i] = (const char*)src_ptrs[i];
+    dst[i] = (char*)dst_ptrs[i];
+    if (kind != 0) {
+      // the host side must be pinned (device-mapped under UVA) to be read / written by a kernel
+      cudaPointerAttributes attr;
+      const void* host = kind == 1 ? (const void*)dst[i] : (const void*)src[i];
+      if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+        cudaGetLastError();
+        mapped = false;
+      } else if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) {
+        mapped = false;
+      } else if (kind == 1) {
+        dst[i] = (char*)attr.devicePointer;
+      } else {
+        src[i] = (const char*)attr.devicePointer;
+      }
+    }
+  }
+  if (mapped)   // every block of every layer in one gather / scatter launch
+    return run_block_copies(src, dst, num_bufs, block_mapping, num_pairs, block_bytes,
+                            (cudaStream_t)stream, "swap_blocks_layers");
+  for (int i = 0; i < num_bufs; ++i) {   // pageable host memory: buffer by buffer, memcpy runs
+    const int rc = vltr_swap_blocks(src_ptrs[i], dst_ptrs[i], kind, block_mapping, num_pairs,
+                                    block_bytes, stream);
+    if (rc != VLTR_OK) return rc;
+  }
+  return VLTR_OK;
+}
+
 extern "C" int vltr_convert_fp8(const void* src, void* dst, int64_t numel, int src_dtype,
                                 int dst_dtype, void* stream) {
   using namespace vltr;

@@ -138,8 +138,8 @@ class B200Sampler(torch.nn.Module):
         for seq_ids, sp in sampling_metadata.seq_groups:
             n = len(seq_ids)
             results.append((toks[row:row + n], list(range(n))))
-            sample_logprobs.append([{toks[row + j]: Logprob(float(torch.tensor(lpl[row + j], dtype=torch.float32)),
-                                                             rkl[row + j])} for j in range(n)])
+            sample_logprobs.append([{toks[row + j]: Logprob(lpl[row + j], rkl[row + j])}
+                                    for j in range(n)])
             row += n
         return _build_sampler_output(results, sampling_metadata,
                                      [None] * len(sampling_metadata.seq_groups), sample_logprobs,

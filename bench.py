@@ -372,6 +372,10 @@ def _main(out):
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="N=1: replay the step from a CUDA graph (default) or issue it kernel by "
                          "kernel (N>1 is always kernel by kernel)")
+    ap.add_argument("--with-gemms", action="store_true",
+                    help="N=1, context only: additionally time the step with the four cuBLAS "
+                         "projections of every layer (seeded random weights) between the ops and "
+                         "report it under \"with_gemms\"")
     ap.add_argument("--no-pdl", action="store_true",
                     help="launch without programmatic dependent launch (A/B)")
     ap.add_argument("--no-tick", dest="tick", action="store_false",
@@ -653,6 +657,27 @@ def _main(out):
         "gpu_launches": int(launches), "roofline": roofline,
         "host_issue_ms_per_step": host_ms, "tick_ms_alone": tick_ms,
     }
+    if args.with_gemms and world == 1:
+        # context, not the metric: the same step with the dense projections (library code) in it
+        hp.enable_gemms()
+        g2, out2 = hp.capture(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                              devin["block_tables"], devin["context_lens"], max_ctx)
+        for _ in range(3):
+            g2.replay()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(args.steps):
+            g2.replay()
+        w1.record()
+        barrier()
+        gms = w0.elapsed_time(w1) / args.steps
+        line["with_gemms"] = {
+            "ms_per_step": gms, "tokens_per_s": args.batch / (gms * 1e-3),
+            "what": "the same decode step with qkv/o/gate_up/down projections of every layer "
+                    "(torch.matmul -> cuBLAS, bf16, seeded random weights, one set per layer) "
+                    "between the ops, replayed from a CUDA graph; no embedding, lm_head, sampler "
+                    "or scheduler tick", "finite": bool(torch.isfinite(out2.float()).all())}
     if rank == 0 and not args.no_cpu_baseline:
         tps, cms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, 2, 1,
                                                         args.cpu_sample_layers,

@@ -163,6 +163,23 @@ class DecodeHotPath:
         self.normed = torch.empty_like(self.hidden)
         self.scale = float(scale)
         self.attn_events = None   # optional [(start, end)] CUDA events around each attention call
+        self.gemm_w = None        # optional per-layer GEMM weights (enable_gemms)
+
+    def enable_gemms(self, seed: int = 1) -> None:
+        """Context for the hot-path numbers: also run the four dense projections of every layer
+        (qkv_proj, o_proj, gate_up_proj, down_proj - library code, cuBLAS via torch.matmul) with
+        seeded random weights of the model's shapes, writing the buffers the ops consume.  The
+        step then is the whole decoder stack of a decode step (no embedding / lm_head / sampler);
+        weights are per layer, so their HBM traffic is real.  Single GPU only."""
+        s = self.shape
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        qkv_w = (s.q_heads + 2 * s.kv_heads) * s.head_size
+
+        def w(n, k):
+            return (torch.randn(n, k, generator=g, device=self.device) * (k ** -0.5)).to(s.dtype)
+
+        self.gemm_w = [(w(qkv_w, s.hidden), w(s.hidden, s.q_heads * s.head_size),
+                        w(2 * s.inter, s.hidden), w(s.hidden, s.inter)) for _ in range(self.layers)]
 
     def capture(self, hidden_in, positions, slot_mapping, block_tables, context_lens,
                 max_context_len: int):
@@ -276,6 +293,9 @@ class DecodeHotPath:
             else:
                 ops.fused_add_rms_norm(hidden, residual, self.norm_w[2 * layer], s.eps)
             # [qkv_proj GEMM writes qkv]
+            gw = self.gemm_w[layer] if self.gemm_w is not None else None
+            if gw is not None:
+                torch.matmul(self.normed[:T] if layer == 0 else hidden, gw[0].t(), out=qkv)
             ops.rotary_embedding(positions, q, k, s.head_size, self.cos_sin, True)
             kc, vc = self.key_caches[layer], self.value_caches[layer]
             cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
@@ -293,13 +313,19 @@ class DecodeHotPath:
                 ev.append((e0, e1))
             # [o_proj GEMM reads attn_out, writes o_proj_out; row-parallel => all-reduce]
             hidden = self.o_proj_out[:T]
+            if gw is not None:
+                torch.matmul(attn_out, gw[1].t(), out=hidden)
             if all_reduce is not None:
                 all_reduce(hidden)
             ops.fused_add_rms_norm(hidden, residual, self.norm_w[2 * layer + 1], s.eps)
             # [gate_up_proj GEMM writes gate_up]
+            if gw is not None:
+                torch.matmul(hidden, gw[2].t(), out=self.gate_up[:T])
             ops.silu_and_mul(self.act_out[:T], self.gate_up[:T])
             # [down_proj GEMM reads act_out, writes down_out; row-parallel => all-reduce]
             hidden = self.down_out[:T]
+            if gw is not None:
+                torch.matmul(self.act_out[:T], gw[3].t(), out=hidden)
             if all_reduce is not None:
                 all_reduce(hidden)
         ops.fused_add_rms_norm(hidden, residual, self.norm_w[2 * self.layers], s.eps)

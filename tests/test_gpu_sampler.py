@@ -2,7 +2,6 @@
 (tests/golden/sampler_ref.npz), against the oracle on seeded inputs at the real vocabulary sizes,
 and - for the in-kernel Philox noise, which no reference run can reproduce - through the
 distribution it must follow."""
-import numpy as np
 import pytest
 import torch
 

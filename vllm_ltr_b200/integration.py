@@ -1,0 +1,79 @@
+"""One call that applies every seam of INTEGRATION.md to a built reference engine.
+
+    import vllm_ltr_b200
+    vllm_ltr_b200.install()                 # before `import vllm`: vllm._C -> libvllm_ltr_b200.so
+    from vllm import LLM
+    llm = LLM(...)                          # the unmodified reference engine
+    from vllm_ltr_b200.integration import install_engine
+    print(install_engine(llm.llm_engine))   # scheduler tick, predictor, swap path, decode inputs, sampler
+
+Each piece is optional and reported; pieces whose preconditions do not hold (schedule_type is not
+"opt*", no predictor configured, Ray workers instead of an in-process driver worker) are skipped
+with the reason, never silently replaced by something else.
+"""
+from typing import Dict
+
+
+def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap: bool = True,
+                   decode_inputs: bool = True, sampler: bool = True, prefill: bool = True,
+                   sampler_seed: int = 0) -> Dict[str, str]:
+    done: Dict[str, str] = {}
+    sched = getattr(engine, "scheduler", None)
+
+    if scheduler:
+        st = getattr(sched, "schedule_type", "") if sched is not None else ""
+        if sched is not None and st.startswith("opt"):
+            from . import ltr_scheduler
+            ltr_scheduler.install(sched)
+            done["scheduler"] = "LTR tick: CUDA rank kernel + linear host logic (scheduler.py:969-1502)"
+        else:
+            done["scheduler"] = f"skipped: schedule_type {st!r} is not an LTR ('opt*') policy"
+
+    if predictor:
+        cfg = getattr(getattr(engine, "model_config", None), "prefill_predictor_model_config", None)
+        if sched is not None and cfg is not None and getattr(sched, "aux_model", None) is not None:
+            from .predictor import B200AuxModel
+            sched.aux_model = B200AuxModel.from_pretrained(cfg.path, tokenizer=cfg.pred_model,
+                                                           max_length=cfg.max_length)
+            done["predictor"] = "B200AuxModel (tcgen05 OPT forward) behind scheduler.aux_model"
+        else:
+            done["predictor"] = "skipped: no prefill predictor configured on this engine"
+
+    worker = getattr(getattr(engine, "model_executor", None), "driver_worker", None)
+    runner = getattr(worker, "model_runner", None)
+    if worker is None or runner is None:
+        why = "skipped: no in-process driver worker (apply on every worker process instead)"
+        for k, on in (("swap", swap), ("decode_inputs", decode_inputs), ("sampler", sampler)):
+            if on:
+                done[k] = why
+    else:
+        if swap:
+            ce = getattr(worker, "cache_engine", None)
+            if ce is not None:
+                from ._C.cache_ops import install_cache_engine
+                install_cache_engine(ce)
+                done["swap"] = "CacheEngine.swap_in/out: all layers in one gather/scatter launch"
+            else:
+                done["swap"] = "skipped: cache engine not initialised yet"
+        if decode_inputs:
+            from . import model_runner as mr
+            mr.install(runner)
+            done["decode_inputs"] = "ModelRunner._prepare_decode: vectorised builder"
+        if sampler:
+            model = getattr(runner, "model", None)
+            if model is not None and hasattr(model, "sampler"):
+                from .sampler import B200Sampler
+                model.sampler = B200Sampler(seed=sampler_seed)
+                done["sampler"] = ("B200Sampler (greedy / temperature requests; others raise "
+                                   "NotImplementedError)")
+            else:
+                done["sampler"] = "skipped: model has no .sampler attribute"
+
+    if prefill:
+        try:
+            from . import prefix_prefill
+            prefix_prefill.install()
+            done["prefill"] = "context_attention_fwd (Triton) -> vltr_context_attention_fwd"
+        except ImportError as e:      # the reference's attention package is not importable here
+            done["prefill"] = f"skipped: {e}"
+    return done

@@ -60,6 +60,24 @@ class PythonRanker:
         return np.asarray(idx, dtype=np.int32)
 
 
+import time as _time
+
+
+class NumpyRanker:
+    """Stable order of (pri, -score): what the CUDA rank kernel returns (tests/test_gpu_ltr.py)."""
+    seconds = 0.0      # accumulated time spent ranking (tools/sched_tick_bench.py reports it)
+
+    def order(self, scores, pri=None, negate=True):
+        t0 = _time.perf_counter()
+        key = -np.asarray(scores, dtype=np.float64) if negate else np.asarray(scores, dtype=np.float64)
+        if pri is None:
+            idx = np.argsort(key, kind="stable")
+        else:
+            idx = np.lexsort((key, np.asarray(pri)))       # last key is the primary one; stable
+        NumpyRanker.seconds += _time.perf_counter() - t0
+        return idx.astype(np.int32)
+
+
 def make_population(n, seed, max_prompt=96, max_out=48):
     rng = np.random.default_rng(seed)
     prompt = np.clip(np.rint(np.exp(rng.normal(3.0, 0.8, n))), 2, max_prompt).astype(int)

@@ -122,3 +122,16 @@ def test_tick_cost_is_linear():
     assert res[False][1] == res[True][1]
     print(f"tick @10k live: reference {res[False][0]*1e3:.1f} ms, plugin {res[True][0]*1e3:.1f} ms")
     assert res[True][0] < res[False][0] / 2
+
+
+def test_numpy_ranker_equals_python_sorted():
+    """The stand-in ranker used by the CPU-side tools orders exactly like the reference's `sorted`
+    expression (scheduler.py:996/998), ties included."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    scores = rng.normal(0, 1, 5000).astype(np.float16).astype(np.float64).tolist()   # many ties
+    pri = rng.choice([-1, 0], 5000).tolist()
+    a, b = R.NumpyRanker(), R.PythonRanker()
+    assert a.order(scores).tolist() == b.order(scores).tolist()
+    assert a.order(scores, pri).tolist() == b.order(scores, pri).tolist()
+    assert a.order(scores, None, negate=False).tolist() == b.order(scores, None, negate=False).tolist()

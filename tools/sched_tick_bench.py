@@ -26,20 +26,7 @@ from vllm.sequence import Logprob, Sequence, SequenceGroup, SequenceStatus  # no
 
 from vllm_ltr_b200 import ltr_scheduler  # noqa: E402
 
-
-class NumpyRanker:
-    """Stable order of (pri, -score): what the CUDA rank kernel returns (tests/test_gpu_ltr.py)."""
-    seconds = 0.0
-
-    def order(self, scores, pri=None, negate=True):
-        t0 = time.perf_counter()
-        key = -np.asarray(scores, dtype=np.float64) if negate else np.asarray(scores, dtype=np.float64)
-        if pri is None:
-            idx = np.argsort(key, kind="stable")
-        else:
-            idx = np.lexsort((key, np.asarray(pri)))       # last key is the primary one; stable
-        NumpyRanker.seconds += time.perf_counter() - t0
-        return idx.astype(np.int32)
+NumpyRanker = R.NumpyRanker
 
 
 def build(n, plugin):

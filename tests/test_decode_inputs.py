@@ -1,4 +1,4 @@
-"""CPU: vllm_ltr_b200.model_runner.prepare_decode against the reference's own
+"""CPU: vllm_ltr_b200.decode_inputs.prepare_decode against the reference's own
 ModelRunner._prepare_decode (vllm/worker/model_runner.py:424-548), field by field, over ragged
 batches, sliding windows and the CUDA-graph padding mode.  Needs /root/reference."""
 import random
@@ -54,7 +54,7 @@ def test_prepare_decode_matches_reference(n, block_size, sliding_window, eager):
     R.import_reference()
     from vllm.worker.model_runner import ModelRunner
 
-    from vllm_ltr_b200 import model_runner as ours
+    from vllm_ltr_b200 import decode_inputs as ours
     metas = _metas(n, n * 31 + block_size, block_size, multi_seq=(n == 7))
     if sum(len(m.seq_data) for m in metas) > 256:
         pytest.skip("beyond the engine's 256-sequence budget")
@@ -76,7 +76,7 @@ def test_empty_batch_and_install():
     R.import_reference()
     from vllm.worker.model_runner import PrepareDecodeMetadata
 
-    from vllm_ltr_b200 import model_runner as ours
+    from vllm_ltr_b200 import decode_inputs as ours
     r = _runner(16, None, True)
     assert ours.prepare_decode(r, []) == PrepareDecodeMetadata.empty()
     ours.install(r)

@@ -15,7 +15,7 @@ def test_install_engine_on_reference_shaped_objects(monkeypatch):
     from vllm.config import CacheConfig, SchedulerConfig
     from vllm.core.scheduler import Scheduler
 
-    from vllm_ltr_b200 import integration, ltr_scheduler, model_runner
+    from vllm_ltr_b200 import decode_inputs, integration, ltr_scheduler
     sc = SchedulerConfig(768, 256, 8192, enable_chunked_prefill=True, schedule_type="opt-xxx")
     cc = CacheConfig(16, 1.0, 1, "auto")
     cc.num_gpu_blocks, cc.num_cpu_blocks = 64, 64
@@ -33,7 +33,7 @@ def test_install_engine_on_reference_shaped_objects(monkeypatch):
     assert sched._schedule.__func__ is ltr_scheduler.general_schedule
     assert done["predictor"].startswith("skipped")
     assert callable(ce.swap_in) and callable(ce.swap_out)
-    assert runner._prepare_decode.__func__ is model_runner.prepare_decode
+    assert runner._prepare_decode.__func__ is decode_inputs.prepare_decode
     assert type(runner.model.sampler).__name__ == "B200Sampler"
 
     fcfs = types.SimpleNamespace(scheduler=types.SimpleNamespace(schedule_type="fcfs"),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Host time of ModelRunner._prepare_decode (vllm/worker/model_runner.py:424-548) vs
-vllm_ltr_b200.model_runner.prepare_decode for the bench batch (256 running sequences of the
+vllm_ltr_b200.decode_inputs.prepare_decode for the bench batch (256 running sequences of the
 trace).  CPU only; needs /root/reference.
 
     python tools/prepare_decode_bench.py > profiles/r01_prepare_decode.txt
@@ -24,7 +24,7 @@ from vllm.sequence import SequenceData, SequenceGroupMetadata  # noqa: E402
 from vllm.worker.model_runner import ModelRunner  # noqa: E402
 
 from bench import trace_contexts  # noqa: E402
-from vllm_ltr_b200 import model_runner as ours  # noqa: E402
+from vllm_ltr_b200 import decode_inputs as ours  # noqa: E402
 
 for B in (64, 256):
     ctx = trace_contexts(B)

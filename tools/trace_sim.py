@@ -8,7 +8,7 @@ measurements in profiles/.
 Per simulated step:
   host   Scheduler.schedule() of the reference (/root/reference/vllm/core/scheduler.py), with its
          own LTR methods or with vllm_ltr_b200.ltr_scheduler installed   - executed, wall time
-         ModelRunner._prepare_decode (reference) or vllm_ltr_b200.model_runner.prepare_decode on
+         ModelRunner._prepare_decode (reference) or vllm_ltr_b200.decode_inputs.prepare_decode on
          the step's decode requests                                         - executed, wall time
   gpu    t = base + per_ctx_token * (sum of the contexts of the scheduled sequences)
          ours:      base 4.6 ms, 25 ns/token   (Llama-3-8B: 3.2 ms cuBLAS projections + 1.4 ms small
@@ -42,7 +42,7 @@ from vllm.core.scheduler import Scheduler  # noqa: E402
 from vllm.sequence import Logprob, Sequence, SequenceGroup, SequenceStatus  # noqa: E402
 from vllm.worker.model_runner import ModelRunner  # noqa: E402
 
-from vllm_ltr_b200 import ltr_scheduler, model_runner  # noqa: E402
+from vllm_ltr_b200 import decode_inputs, ltr_scheduler  # noqa: E402
 
 NumpyRanker = R.NumpyRanker     # stand-in for the CUDA rank kernel (no GPU in this container)
 
@@ -70,7 +70,7 @@ def run(arm, n, stop_after, gpu_blocks):
         attn_backend=types.SimpleNamespace(make_metadata=lambda **kw: None))
     if arm == "ours":
         ltr_scheduler.install(sched, ranker=NumpyRanker())
-        prepare = model_runner.prepare_decode
+        prepare = decode_inputs.prepare_decode
     else:
         prepare = ModelRunner._prepare_decode
     for i in range(n):

@@ -56,7 +56,7 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
             else:
                 done["swap"] = "skipped: cache engine not initialised yet"
         if decode_inputs:
-            from . import model_runner as mr
+            from . import decode_inputs as mr
             mr.install(runner)
             done["decode_inputs"] = "ModelRunner._prepare_decode: vectorised builder"
         if sampler:

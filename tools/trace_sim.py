@@ -10,6 +10,10 @@ Per simulated step:
          own LTR methods or with vllm_ltr_b200.ltr_scheduler installed   - executed, wall time
          ModelRunner._prepare_decode (reference) or vllm_ltr_b200.decode_inputs.prepare_decode on
          the step's decode requests                                         - executed, wall time
+         the sampler's host-side tensor preparation: the reference's
+         SamplingTensors.from_sampling_metadata (sampling_metadata.py:79-330, pads every
+         sequence's prompt and output tokens into [batch, max_len] matrices even when no penalty
+         is requested) or the two per-row lists B200Sampler.forward builds    - executed, wall time
   gpu    t = base + per_ctx_token * (sum of the contexts of the scheduled sequences)
          ours:      base 4.6 ms, 25 ns/token   (Llama-3-8B: 3.2 ms cuBLAS projections + 1.4 ms small
                     kernels, attention 82 us x 32 layers per 103 k context tokens;
@@ -41,6 +45,12 @@ from vllm.config import CacheConfig, SchedulerConfig  # noqa: E402
 from vllm.core.scheduler import Scheduler  # noqa: E402
 from vllm.sequence import Logprob, Sequence, SequenceGroup, SequenceStatus  # noqa: E402
 from vllm.worker.model_runner import ModelRunner  # noqa: E402
+import torch  # noqa: E402
+import vllm.model_executor.sampling_metadata as smd  # noqa: E402
+from vllm.model_executor.sampling_metadata import SamplingMetadata, SamplingTensors  # noqa: E402
+from vllm.sampling_params import SamplingType  # noqa: E402
+
+smd.is_pin_memory_available = lambda: False      # no CUDA driver in the build container
 
 from vllm_ltr_b200 import decode_inputs, ltr_scheduler  # noqa: E402
 
@@ -57,7 +67,7 @@ def population(n, seed=0):
     return prompt, out, score
 
 
-def run(arm, n, stop_after, gpu_blocks):
+def run(arm, n, stop_after, gpu_blocks, sampler_host=True):
     prompt, out_len, score = population(n)
     sc = SchedulerConfig(768, 256, 8192, enable_chunked_prefill=True, schedule_type="opt-xxx")
     cc = CacheConfig(16, 1.0, 1, "auto")
@@ -87,6 +97,21 @@ def run(arm, n, stop_after, gpu_blocks):
         decode = [m for m in metas if not m.is_prompt]
         if decode:
             prepare(fake_runner, decode)
+        if sampler_host:
+            if arm == "ours":      # what B200Sampler.forward does on the host before its kernel
+                temps, rnd = [], []
+                for m in metas:
+                    sp = m.sampling_params
+                    k = len(m.seq_data)
+                    temps += [sp.temperature if sp.temperature >= 1e-5 else 1.0] * k
+                    rnd += [int(sp.sampling_type == SamplingType.RANDOM)] * k
+            else:
+                seq_data = {}
+                for m in metas:
+                    seq_data.update(m.seq_data)
+                md = SamplingMetadata([(list(m.seq_data.keys()), m.sampling_params) for m in metas],
+                                      seq_data, [], torch.empty(0, dtype=torch.long), None)
+                SamplingTensors.from_sampling_metadata(md, 32000, torch.device("cpu"), torch.float16)
         h = time.perf_counter() - t0
         ctx = 0
         for s_ in outs.scheduled_seq_groups:
@@ -122,18 +147,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=2000)
     ap.add_argument("--stop-after", type=int, default=0, help="stop after this many completions")
+    ap.add_argument("--no-sampler-host", dest="sampler_host", action="store_false",
+                    help="leave the sampler's host-side tensor preparation out of the step")
     ap.add_argument("--gpu-blocks", type=int, default=60000,
                     help="KV pool in 16-token blocks (Llama-3-8B bf16 on 180 GB: ~60 k)")
     args = ap.parse_args()
     print(f"# simulated LTR run: {args.n} requests at t=0, stop after "
           f"{args.stop_after or 'all'} completions, {args.gpu_blocks} KV blocks; host code executed "
-          f"and timed on this CPU, GPU step time modelled (see the header of tools/trace_sim.py)")
+          f"and timed on this CPU, GPU step time modelled (see the header of tools/trace_sim.py)"
+          f"{'' if args.sampler_host else '; sampler host work excluded'}")
     for arm in ("reference", "ours"):
-        r = run(arm, args.n, args.stop_after, args.gpu_blocks)
+        r = run(arm, args.n, args.stop_after, args.gpu_blocks, args.sampler_host)
         print(f"{r['arm']:9s}: {r['completed']} requests, {r['generated']} output tokens in "
               f"{r['elapsed']:.1f} s simulated = {r['tokens_per_s']:.0f} tokens/s; request latency "
               f"p50 {r['p50']:.1f} s, p90 {r['p90']:.1f} s; {r['steps']} steps, per step: host "
-              f"{r['host_ms']:.1f} ms (schedule + decode inputs, measured), GPU {r['gpu_ms']:.1f} ms "
+              f"{r['host_ms']:.1f} ms (schedule + decode inputs"
+              f"{' + sampler tensors' if args.sampler_host else ''}, measured), GPU {r['gpu_ms']:.1f} ms "
               f"(model)", flush=True)
 
 

@@ -61,3 +61,17 @@ def test_algorithmic_byte_formulas():
     assert step_bytes(ctx, s, 16, 2) > 2 * attention_bytes(ctx, s, 16)
     c = trace_contexts(256)
     assert len(c) == 256 and c.min() >= 1 and c.max() <= 8192 and int(c.sum()) == 103012
+
+
+def test_tensor_parallel_shapes():
+    """Megatron split of the reference (llama.py:96-111): q heads and MLP width divided, kv heads
+    divided or replicated."""
+    s70 = SHAPES["llama-2-70b"].shard(8)
+    assert (s70.q_heads, s70.kv_heads, s70.inter, s70.hidden) == (8, 1, 3584, 8192)
+    s7 = SHAPES["llama-2-7b"].shard(8)
+    assert (s7.q_heads, s7.kv_heads, s7.inter) == (4, 4, 1376)
+    s8 = SHAPES["llama-3-8b"].shard(4)
+    assert (s8.q_heads, s8.kv_heads, s8.inter) == (8, 2, 3584)
+    assert SHAPES["llama-3-8b"].shard(1) is SHAPES["llama-3-8b"]
+    s16 = ModelShape("x", 1024, 2, 16, 2, 64, 2048, torch.bfloat16).shard(8)
+    assert (s16.q_heads, s16.kv_heads) == (2, 1)          # kv heads replicated below one per rank

@@ -9,7 +9,11 @@ import sys
 
 import numpy as np
 
-REF = "/root/reference"
+# the reference's Python package: the checkout in the build container, or the unmodified copy
+# `make -C oracle vllm_py` ships to the GPU box (oracle/_ref/vllm_py, git-ignored)
+_SHIPPED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "oracle", "_ref", "vllm_py")
+REF = "/root/reference" if os.path.isdir("/root/reference/vllm/core") else _SHIPPED
 
 
 def have_reference() -> bool:

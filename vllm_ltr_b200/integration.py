@@ -14,9 +14,26 @@ with the reason, never silently replaced by something else.
 from typing import Dict
 
 
+def _release_aux_engine(aux) -> None:
+    """Drop the reference's second engine (AUXLLM -> AUXLLMEngine -> its own worker and a copy of
+    the OPT weights on the GPU, llm_engine.py:228-242) once B200AuxModel has taken its place."""
+    eng = getattr(aux, "llm_engine", None)
+    worker = getattr(getattr(eng, "model_executor", None), "driver_worker", None)
+    runner = getattr(worker, "model_runner", None)
+    if runner is not None and hasattr(runner, "model"):
+        runner.model = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+    except ImportError:
+        pass
+
+
 def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap: bool = True,
                    decode_inputs: bool = True, sampler: bool = True, prefill: bool = True,
-                   sampler_seed: int = 0) -> Dict[str, str]:
+                   sampler_seed: int = 0,
+                   release_reference_predictor: bool = True) -> Dict[str, str]:
     done: Dict[str, str] = {}
     sched = getattr(engine, "scheduler", None)
 
@@ -30,11 +47,20 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
             done["scheduler"] = f"skipped: schedule_type {st!r} is not an LTR ('opt*') policy"
 
     if predictor:
+        # model_config.prefill_predictor_model_config is a PrefillPredictorConfig whose only
+        # attribute is `.model` (a PrefillModelConfig, vllm/config_predictor.py:38-46,131-143);
+        # the reference reads .model.path / .model.pred_model / .model.max_length
+        # (llm_engine.py:225-242).
         cfg = getattr(getattr(engine, "model_config", None), "prefill_predictor_model_config", None)
-        if sched is not None and cfg is not None and getattr(sched, "aux_model", None) is not None:
+        m = getattr(cfg, "model", None)
+        if sched is not None and m is not None and getattr(sched, "aux_model", None) is not None:
             from .predictor import B200AuxModel
-            sched.aux_model = B200AuxModel.from_pretrained(cfg.path, tokenizer=cfg.pred_model,
-                                                           max_length=cfg.max_length)
+            old = sched.aux_model
+            sched.aux_model = B200AuxModel.from_pretrained(
+                m.path, tokenizer=m.pred_model, max_length=m.max_length,
+                max_batch_prompts=min(int(getattr(m, "max_batch_size", 256) or 256), 256))
+            if release_reference_predictor:
+                _release_aux_engine(old)
             done["predictor"] = "B200AuxModel (tcgen05 OPT forward) behind scheduler.aux_model"
         else:
             done["predictor"] = "skipped: no prefill predictor configured on this engine"

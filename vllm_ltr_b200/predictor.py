@@ -10,8 +10,8 @@ the predictor's tokenizer, truncated to ``max_model_len``), the model's logits, 
 forward pass done by ``libvllm_ltr_b200`` (csrc/opt_predictor.cu: tcgen05 GEMMs with fused
 epilogues, one stream, no host sync until the scores are read).
 
-    aux = B200AuxModel.from_pretrained(cfg.path, tokenizer=cfg.pred_model, max_length=cfg.max_length,
-                                       mtype=cfg.mtype)            # PrefillPredictorConfig fields
+    m = model_config.prefill_predictor_model_config.model          # PrefillModelConfig
+    aux = B200AuxModel.from_pretrained(m.path, tokenizer=m.pred_model, max_length=m.max_length)
     engine.scheduler.aux_model = aux                                # llm_engine.py:228-242
 """
 import ctypes
@@ -260,14 +260,14 @@ class OPTPredictor:
         host = self._host[:need]
         ids, pos = host[:m], host[m:2 * m]
         cu, last = host[2 * m:2 * m + n + 1], host[2 * m + n + 1:]
-        o = 0
-        cu[0] = 0
-        for k, p in enumerate(batch):
-            ids[o:o + lens[k]] = torch.as_tensor(p, dtype=torch.int32)
-            pos[o:o + lens[k]] = torch.arange(lens[k], dtype=torch.int32)
-            o += lens[k]
-            cu[k + 1] = o
-            last[k] = o - 1
+        import numpy as np
+        la = np.asarray(lens, dtype=np.int64)
+        ends = np.cumsum(la)
+        ids.numpy()[:] = np.fromiter((t for p in batch for t in p), dtype=np.int32, count=m)
+        pos.numpy()[:] = np.arange(m, dtype=np.int64) - np.repeat(ends - la, la)
+        cu.numpy()[0] = 0
+        cu.numpy()[1:] = ends
+        last.numpy()[:] = ends - 1
         d = host.to(self.device, non_blocking=True)
         self._host_evt = torch.cuda.Event()
         self._host_evt.record()
@@ -294,26 +294,36 @@ class B200AuxModel:
     that calls ``set_aux_model_score`` on each group (aux_llm_engine.py:332-412)."""
 
     def __init__(self, predictor: OPTPredictor, tokenizer: Callable[[str], List[int]],
-                 max_length: int = 2048):
+                 max_length: int = 2048,
+                 batch_tokenizer: Optional[Callable[[List[str]], List[List[int]]]] = None):
         self.predictor = predictor
         self.tokenizer = tokenizer
+        self.batch_tokenizer = batch_tokenizer
         self.max_length = max_length
 
     @classmethod
     def from_pretrained(cls, path: str, tokenizer=None, max_length: int = 2048, **kw):
         pred = OPTPredictor.from_pretrained(path, **kw)
+        batch = None
         if tokenizer is None or isinstance(tokenizer, str):
             from transformers import AutoTokenizer
             hf = AutoTokenizer.from_pretrained(tokenizer or path)
             tokenizer = lambda text: hf.encode(text)
-        return cls(pred, tokenizer, max_length)
+            if getattr(hf, "is_fast", False):
+                # same ids as encode() one by one (tokenizer.encode == tokenizer(text).input_ids),
+                # tokenised in parallel by the Rust backend
+                batch = lambda texts: hf(texts, add_special_tokens=True)["input_ids"]
+        return cls(pred, tokenizer, max_length, batch)
 
     def obtain_aux_scores(self, seq_groups) -> List[float]:
-        prompts = []
+        texts = []
         for sg in seq_groups:
             assert sg.need_aux_model_score()
-            text = sg.seqs_dict[next(iter(sg.seqs_dict))].prompt
-            prompts.append(list(self.tokenizer(text))[:self.max_length])
+            texts.append(sg.seqs_dict[next(iter(sg.seqs_dict))].prompt)
+        if self.batch_tokenizer is not None and len(texts) > 1:
+            prompts = [list(p)[:self.max_length] for p in self.batch_tokenizer(texts)]
+        else:
+            prompts = [list(self.tokenizer(t))[:self.max_length] for t in texts]
         scores = self.predictor.scores(prompts)
         for sg, s in zip(seq_groups, scores):
             sg.set_aux_model_score(s)

@@ -171,7 +171,7 @@ def opt_state_dict(kind: str, seed: int):
 # the trace (BASELINE.md section 4)
 # --------------------------------------------------------------------------------------------
 def make_trace(n: int, vocab: int, max_len: int, seed: int = 0, tau: float = 0.52,
-               max_output: Optional[int] = None):
+               max_output: Optional[int] = None, min_output: Optional[int] = None):
     """[(prompt text, prompt_len, output_len, ordering score)]; prompt_len counts the BOS the
     tokenizer prepends.  Scores are -log(output_len) + N(0, sigma), sigma bisected so that Kendall
     tau(score, -output_len) = `tau`, rounded to fp16 (forces ties)."""
@@ -180,6 +180,8 @@ def make_trace(n: int, vocab: int, max_len: int, seed: int = 0, tau: float = 0.5
     plen = np.clip(np.round(np.exp(rng.normal(5.0, 1.0, n))), 4, 2048).astype(np.int64)
     olen = np.round(np.exp(rng.normal(5.3, 1.1, n))).astype(np.int64)
     olen = np.clip(olen, 4, np.minimum(8192, max_len) - plen)
+    if min_output is not None:
+        olen = np.maximum(olen, min_output)
     if max_output is not None:
         olen = np.minimum(olen, max_output)
     noise = rng.normal(0.0, 1.0, n)
@@ -280,21 +282,19 @@ def _transformers5_compat() -> None:
 
 
 def reinit_weights(model, seed: int = 0, std: float = 0.02) -> None:
-    """Replace the dummy loader's U(-1e-3, 1e-3) tensors by seeded N(0, std) (norm weights 1):
-    same values in both arms (generated on the CPU generator, parameter by parameter)."""
+    """Replace the dummy loader's U(-1e-3, 1e-3) tensors by seeded N(0, std) (norm weights 1).
+    Drawn parameter by parameter in name order from one seeded generator on the parameters' own
+    device, so both arms (same box, same GPU type) get the same values."""
     import torch
-    g = torch.Generator().manual_seed(seed)
+    params = sorted(model.named_parameters(), key=lambda kv: kv[0])
+    dev = params[0][1].device
+    g = torch.Generator(device=dev).manual_seed(seed)
     with torch.no_grad():
-        for name, p in sorted(model.named_parameters(), key=lambda kv: kv[0]):
+        for name, p in params:
             if name.endswith("norm.weight") or "layernorm.weight" in name:
                 p.fill_(1.0)
-                continue
-            # draw in chunks to keep host memory small; values depend only on (seed, name order)
-            flat = p.data.view(-1)
-            step = 1 << 24
-            for s in range(0, flat.numel(), step):
-                n = min(step, flat.numel() - s)
-                flat[s:s + n].copy_((torch.randn(n, generator=g) * std).to(p.dtype))
+            else:
+                p.normal_(0.0, std, generator=g)
 
 
 def build_llm(arm: str, assets: Dict[str, str], num_stop: int, schedule: str = "opt-xxx",
@@ -468,6 +468,7 @@ def main():
     ap.add_argument("--stop-after", type=int, default=1000,
                     help='N of "opt-xxx-synthetic((-1,-1,N),)"; 0 = run every request to the end')
     ap.add_argument("--max-output", type=int, default=None)
+    ap.add_argument("--min-output", type=int, default=None)
     ap.add_argument("--scores", choices=["synthetic", "predictor"], default="synthetic")
     ap.add_argument("--kv-cache-dtype", default="auto")
     ap.add_argument("--gpu-memory-utilization", type=float, default=0.9)
@@ -484,7 +485,7 @@ def main():
     assets = make_assets(args.assets, args.model, args.predictor, args.layers)
     cfg = dict(LLAMA[args.model])
     reqs = make_trace(args.num_prompts, cfg["vocab_size"], cfg["max_position_embeddings"],
-                      max_output=args.max_output)
+                      max_output=args.max_output, min_output=args.min_output)
     llm, info = build_llm(args.arm, assets, args.stop_after, kv_cache_dtype=args.kv_cache_dtype,
                           gpu_memory_utilization=args.gpu_memory_utilization,
                           swap_space=args.swap_space,

@@ -4,13 +4,12 @@
 Metric (BASELINE.json): output tokens/s on a ShareGPT-shaped trace.  One "step" = one engine
 decode step of the hot path for a batch of B running sequences (one new token each): for every
 decoder layer  fused_add_rms_norm -> rotary_embedding -> reshape_and_cache -> paged_attention ->
-fused_add_rms_norm -> silu_and_mul, then the final norm (vllm_ltr_b200/hotpath.py; the cuBLAS
+fused_add_rms_norm -> silu_and_mul, then the final norm (tools/hotpath.py; the cuBLAS
 GEMMs between them are library code outside this path and are NOT executed or counted).
 Contexts are the running contexts of a synthetic ShareGPT-shaped trace.
 
   value     tokens/s with every input already resident in HBM (CUDA events, max over ranks);
-            at N=1 the step is replayed from a CUDA graph (DecodeHotPath.capture), at N>1 it is
-            issued kernel by kernel
+            the step is replayed from a CUDA graph (DecodeHotPath.capture) at every N
   e2e       the same step driven from HOST buffers: per step the engine's host-built inputs
             (positions, slot_mapping, block_tables, context_lens, token hidden rows) are copied
             from pinned memory, and the final-norm output is read back, inside the timed region
@@ -19,8 +18,24 @@ Contexts are the running contexts of a synthetic ShareGPT-shaped trace (BASELINE
   cpu_baseline / --impl reference: the reference's own CPU kernels (csrc/cpu, built into
             oracle/_ref by oracle/Makefile) driven through the same call sequence on host cores.
 
+  ref_cuda  (N=1) the same step, pools and inputs driven through the REFERENCE's CUDA kernels
+            recompiled for sm_100a (oracle/_ref/ref_cuda_C: the "reference CUDA build" target of
+            BASELINE.md section 3.1), replayed from a CUDA graph like ours, with its own clocks;
+            `models` repeats the ours / ref_cuda pair for Llama-3-8B and Llama-3-8B + e5m2 KV
+  with_gemms  the step with the four cuBLAS projections of every layer between the ops
+  trace     (N=1) the reference's real metric: the UNMODIFIED reference engine
+            (oracle/_ref/vllm_py) runs the synthetic ShareGPT trace of BASELINE.md section 4 -
+            10 000 requests at t=0, "opt-xxx-synthetic((-1,-1,1000),)", chunked prefill, eager,
+            dummy-weight Llama-2-7B + OPT-125M predictor - once with the reference's CUDA kernels
+            and stock scheduler / predictor engine and once with vllm_ltr_b200.install() +
+            install_engine(); output tokens/s and p50 request latency of both
+            (tools/engine_trace.py, one subprocess per arm)
+
 N > 1 (torchrun): tensor-parallel shards of the same model (q/kv heads and MLP width divided,
-two all-reduces of [B, hidden] per layer over NCCL), scaling = "strong".
+two exchanges of [B, hidden] per layer, fused with the residual add + RMSNorm that follows),
+scaling = "strong"; the step replays from a CUDA graph on every rank in lockstep.  Before
+timing, the fused exchange is checked bit-exactly against NCCL on integer-valued inputs
+(`tp_parity`); at 8 GPUs the Llama-2-70B TP8 shapes are measured as well (`config_70b`).
 """
 import argparse
 import glob
@@ -38,6 +53,9 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+TOOLS = os.path.join(ROOT, "tools")      # bench / test drivers (hotpath.py, engine_trace.py)
+if TOOLS not in sys.path:
+    sys.path.insert(1, TOOLS)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -284,7 +302,7 @@ def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_bat
     """Times the reference CPU kernels on a bounded sample: `sample_batch` sequences of the same
     trace x `sample_layers` layers per step, scaled to the full layer count.  Returns
     (tokens/s, ms per full step, description, cores, kind)."""
-    from vllm_ltr_b200.hotpath import DecodeHotPath, ModelShape
+    from hotpath import DecodeHotPath, ModelShape
     mod, kind = load_ref_cpu()
     if mod is None:
         mod = OraclePort()
@@ -344,6 +362,226 @@ def cpu_reference_run(args, shape, ctx, steps, warmup, sample_layers, sample_bat
 
 
 # ---------------------------------------------------------------------------------------------
+# secondary arms (N=1): reference CUDA kernels on the same step, other models, the engine trace
+# ---------------------------------------------------------------------------------------------
+def load_ref_cuda():
+    """The reference's CUDA kernels recompiled unmodified for sm_100a (oracle/_ref/ref_cuda_C,
+    built by oracle/Makefile) - a checker / baseline, never on the product path."""
+    hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", "ref_cuda_C.*.so"))
+    if not hits:
+        return None
+    spec = importlib.util.spec_from_file_location("ref_cuda_C", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+def time_step_graph(hp, devin, max_ctx, steps):
+    """ms per step of the graph-replayed decode step (inputs resident, no tick)."""
+    g, _ = hp.capture(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                      devin["block_tables"], devin["context_lens"], max_ctx)
+    for _ in range(3):
+        g.replay()
+    _sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.replay()
+    e1.record()
+    _sync()
+    return e0.elapsed_time(e1) / steps
+
+
+def time_attention_b2b(hp, devin, max_ctx, batch, steps):
+    for _ in range(2):
+        hp.attention_only(devin["block_tables"], devin["context_lens"], max_ctx, batch)
+    _sync()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(steps):
+        hp.attention_only(devin["block_tables"], devin["context_lens"], max_ctx, batch)
+    a1.record()
+    _sync()
+    return a0.elapsed_time(a1) / (steps * hp.layers)
+
+
+def step_pair(name, batch, steps, dev, ref, peak, clocks, ours=True, layers=None):
+    """ours / ref_cuda on the decode step of model `name`: same pools, same inputs, graph replay."""
+    from hotpath import SHAPES, DecodeHotPath, ModelShape
+    shape = ModelShape(**{**SHAPES[name].__dict__})
+    if shape.dtype == torch.float16:
+        shape.dtype = torch.bfloat16
+    if layers:
+        shape.layers = layers
+    ctx = trace_contexts(batch)
+    bs = shape.block_size
+    nb = int(((ctx + bs - 1) // bs).sum()) + 64
+    devin = {k: v.to(dev) for k, v in build_inputs(ctx, bs, nb, 0).items()}
+    g = torch.Generator().manual_seed(0)
+    devin["hidden"] = (torch.randn(batch, shape.hidden, generator=g) * 0.5).to(shape.dtype).to(dev)
+    max_ctx = int(ctx.max())
+    abytes = attention_bytes(ctx, shape, bs)
+    res = {"model": name, "batch": batch, "layers": shape.layers,
+           "attention_algorithmic_bytes": abytes}
+    arms = ([("ours", None)] if ours else []) + ([("ref_cuda", ref)] if ref is not None else [])
+    for label, mod in arms:
+        hp = DecodeHotPath(shape, nb, batch, dev, C=mod)
+        for _ in range(3):
+            hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                    devin["block_tables"], devin["context_lens"], max_ctx)
+        _sync()
+        t0 = time.time()
+        ms = time_step_graph(hp, devin, max_ctx, steps)
+        a_ms = time_attention_b2b(hp, devin, max_ctx, batch, steps)
+        t1 = time.time()
+        res[label] = {"ms_per_step": ms, "tokens_per_s": batch / (ms * 1e-3),
+                      "attention_launch_ms": a_ms,
+                      "attention_gbs": abytes / (a_ms * 1e-3) / 1e9,
+                      "attention_roofline_frac": abytes / (a_ms * 1e-3) / 1e9 / peak,
+                      "clocks": clocks.summary(t0, t1)}
+        del hp
+        torch.cuda.empty_cache()
+    if "ours" in res and "ref_cuda" in res:
+        res["speedup_vs_ref_cuda"] = res["ref_cuda"]["ms_per_step"] / res["ours"]["ms_per_step"]
+    return res
+
+
+def run_trace_arm(arm, args, clocks, timeout_s):
+    """One arm of the engine-level trace in its own process (vllm._C is bound per process)."""
+    out = os.path.join("/tmp", f"vltr_trace_{arm}_{os.getpid()}.json")
+    cmd = [sys.executable, os.path.join(TOOLS, "engine_trace.py"), "--arm", arm,
+           "--model", args.trace_model, "--num-prompts", str(args.trace_prompts),
+           "--stop-after", str(args.trace_stop), "--json", out]
+    t0 = time.time()
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s:.0f} s"}
+    t1 = time.time()
+    if r.returncode != 0 or not os.path.exists(out):
+        return {"error": f"rc={r.returncode}", "tail": r.stdout[-1500:]}
+    with open(out) as f:
+        d = json.load(f)
+    os.unlink(out)
+    s = d["summary"]
+    keep = ("tokens_per_s", "p50_latency_s", "p90_latency_s", "requests_per_s", "finished",
+            "generated_tokens", "elapsed_s", "steps", "schedule_s", "execute_model_s",
+            "predictor_s", "other_host_s", "add_requests_s")
+    res = {k: s[k] for k in keep}
+    res["engine_init_s"] = d["engine"]["init_s"]
+    res["num_gpu_blocks"] = d["engine"]["num_gpu_blocks"]
+    res["wall_s"] = t1 - t0
+    res["clocks"] = clocks.summary(t1 - s["elapsed_s"], t1)
+    if "installed" in d["engine"]:
+        res["installed"] = sorted(k for k, v in d["engine"]["installed"].items()
+                                  if not v.startswith("skipped"))
+    return res
+
+
+def measure_70b(args, dev, rank, world, peak):
+    """BASELINE.json config 5 at step level: Llama-2-70B shapes sharded TP=`world` (8 q / 1 kv
+    head and inter/8 per GPU, 80 layers, 160 fused exchanges of [B, 8192] per step), same trace
+    batch, graph replay on every rank in lockstep, max over ranks."""
+    import torch.distributed as dist
+    from hotpath import SHAPES, DecodeHotPath, ModelShape
+    from vllm_ltr_b200.parallel import FusedTPComm
+    full = ModelShape(**{**SHAPES["llama-2-70b"].__dict__})
+    full.dtype = torch.bfloat16
+    shape = full.shard(world)
+    ctx = trace_contexts(args.batch)
+    bs = shape.block_size
+    nb = int(((ctx + bs - 1) // bs).sum()) + 64
+    devin = {k: v.to(dev) for k, v in build_inputs(ctx, bs, nb, 0).items()}
+    g = torch.Generator().manual_seed(0)
+    devin["hidden"] = (torch.randn(args.batch, shape.hidden, generator=g) * 0.5).to(shape.dtype).to(dev)
+    max_ctx = int(ctx.max())
+    hp = DecodeHotPath(shape, nb, args.batch, dev, seed=rank)
+    hp.attach_fused_tp(FusedTPComm(args.batch, shape.hidden, shape.dtype, dev))
+    parity = tp_parity_check(hp.comm, dev, rank, world, args.batch, shape.hidden, shape.dtype)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        hp.step(devin["hidden"], devin["positions"], devin["slot_mapping"], devin["block_tables"],
+                devin["context_lens"], max_ctx)
+    barrier()
+    graph, _ = hp.capture(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                          devin["block_tables"], devin["context_lens"], max_ctx)
+    for _ in range(3):
+        graph.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    a_ms = time_attention_b2b(hp, devin, max_ctx, args.batch, args.steps)
+    barrier()
+    t = torch.tensor([ms, a_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, a_ms = float(t[0]), float(t[1])
+    abytes = attention_bytes(ctx, shape, bs)
+    del hp, graph
+    torch.cuda.empty_cache()
+    return {"workload": f"llama-2-70b TP{world} decode hot path, B={args.batch}, {shape.layers} "
+                        "layers, fused exchange+norm, CUDA-graph replay, no tick",
+            "ms_per_step": ms, "tokens_per_s": args.batch / (ms * 1e-3), "tp_parity": parity,
+            "attention_launch_ms": a_ms, "attention_algorithmic_bytes": abytes,
+            "attention_roofline_frac": abytes / (a_ms * 1e-3) / 1e9 / peak,
+            "attention_share_of_step": a_ms * shape.layers / ms}
+
+
+def tp_parity_check(comm, dev, rank, world, T, H, dtype):
+    """Integer-valued exactness of the fused exchange against NCCL (the reference's own test of
+    its custom all-reduce: tests/distributed/test_custom_all_reduce.py:30-51): the plain sum must
+    equal dist.all_reduce bit for bit, the fused residual too, and the normalised rows must
+    equal our own norm kernel applied to the NCCL sum.  Returns "exact" or raises."""
+    import torch.distributed as dist
+    from vllm_ltr_b200 import _C
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.randint(-4, 5, (T, H), generator=g, device=dev).to(dtype)
+    g0 = torch.Generator(device=dev).manual_seed(7)
+    resid = torch.randint(-4, 5, (T, H), generator=g0, device=dev).to(dtype)
+    w = (torch.randn(H, generator=g0, device=dev) * 0.1 + 1).to(dtype)
+    keep = [t[:T].clone() for t in (comm.x[0], comm.x[1], comm.resid)]
+    s = x.clone()
+    dist.all_reduce(s)
+    want_res = resid.clone()
+    want_out = s.clone()
+    _C.ops.fused_add_rms_norm(want_out, want_res, w, 1e-5)     # residual += sum; out = norm
+    comm.x[1][:T].copy_(x)
+    torch.cuda.synchronize()
+    dist.barrier()
+    plain = comm.allreduce(1, T).clone()
+    comm.x[0][:T].copy_(x)
+    comm.resid[:T].copy_(resid)
+    torch.cuda.synchronize()
+    dist.barrier()
+    out = comm.allreduce_add_rms_norm(0, w, 1e-5, T).clone()
+    torch.cuda.synchronize()
+    ok = torch.tensor([int(torch.equal(plain, s)), int(torch.equal(comm.resid[:T], want_res)),
+                       int(torch.equal(out, want_out))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    for t, k in zip((comm.x[0], comm.x[1], comm.resid), keep):
+        t[:T].copy_(k)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if not bool(ok.all()):
+        raise RuntimeError(f"fused TP exchange differs from NCCL: sum/resid/norm exact = {ok.tolist()}")
+    return "exact"
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     # the driver reads ONE JSON line from stdout: libraries that print there (NCCL's version
     # banner) are pointed at stderr, the line goes to the real stdout at the end
@@ -370,8 +608,7 @@ def _main(out):
     ap.add_argument("--tp-exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused peer-memory all-reduce+norm kernel, or NCCL all_reduce + norm")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
-                    help="N=1: replay the step from a CUDA graph (default) or issue it kernel by "
-                         "kernel (N>1 is always kernel by kernel)")
+                    help="replay the step from a CUDA graph (default) or issue it kernel by kernel")
     ap.add_argument("--with-gemms", action="store_true",
                     help="N=1, context only: additionally time the step with the four cuBLAS "
                          "projections of every layer (seeded random weights) between the ops and "
@@ -383,10 +620,20 @@ def _main(out):
     ap.add_argument("--live-requests", type=int, default=10000,
                     help="live requests ordered per tick (synthetic-sharegpt.sh submits 10000)")
     ap.add_argument("--tick-prompt-len", type=int, default=245)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="only the main line: skip ref_cuda / with_gemms / models / trace")
+    ap.add_argument("--trace", default="both", choices=["both", "ours", "off"],
+                    help="N=1: engine-level trace arms to run (tools/engine_trace.py)")
+    ap.add_argument("--trace-model", default="llama-2-7b")
+    ap.add_argument("--trace-prompts", type=int, default=10000)
+    ap.add_argument("--trace-stop", type=int, default=1000)
+    ap.add_argument("--extras-budget-s", type=float, default=540.0,
+                    help="stop starting secondary measurements once the run is this old")
     args = ap.parse_args()
+    t_run0 = time.time()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    from vllm_ltr_b200.hotpath import SHAPES, ModelShape
+    from hotpath import SHAPES, ModelShape
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -434,7 +681,7 @@ def _main(out):
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     import torch.distributed as dist
     from vllm_ltr_b200._lib import launch_count, tune
-    from vllm_ltr_b200.hotpath import DecodeHotPath
+    from hotpath import DecodeHotPath
     if args.no_pdl:
         tune("pdl", 0)
     torch.cuda.set_device(local_rank)
@@ -455,10 +702,14 @@ def _main(out):
     out_host = torch.empty(args.batch, shape.hidden, dtype=shape.dtype).pin_memory()
 
     all_reduce = None
+    tp_parity = None
     if world > 1:
         if args.tp_exchange == "fused":
             from vllm_ltr_b200.parallel import FusedTPComm
             hp.attach_fused_tp(FusedTPComm(args.batch, shape.hidden, shape.dtype, dev))
+            # parity gate before any timing: a wrong reduction must not produce a number
+            tp_parity = tp_parity_check(hp.comm, dev, rank, world, args.batch, shape.hidden,
+                                        shape.dtype)
         else:
             from vllm_ltr_b200.parallel import tensor_model_parallel_all_reduce
             all_reduce = tensor_model_parallel_all_reduce
@@ -484,6 +735,7 @@ def _main(out):
     # with --tp-exchange nccl the step is issued kernel by kernel.
     use_graph = args.launch == "graph" and (world == 1 or args.tp_exchange == "fused")
     graph = graph_out = None
+    ms_no_tick = None
     launches_per_graph = 0
     if use_graph:
         n_before = launch_count()
@@ -569,6 +821,16 @@ def _main(out):
         barrier()
         launches = launch_count() - n0 + launches_per_graph * args.steps
         ms = g0.elapsed_time(g1)
+        # the same replays without the tick on the side stream (what `ref_cuda` is compared with)
+        for _ in range(2):
+            graph.replay()
+        barrier()
+        g0.record()
+        for _ in range(args.steps):
+            graph.replay()
+        g1.record()
+        barrier()
+        ms_no_tick = g0.elapsed_time(g1) / args.steps
     t_end = time.time()
 
     # host cost of issuing the decode ops of one step (no device wait, tick excluded): must
@@ -597,7 +859,7 @@ def _main(out):
     barrier()
     e2e_s = time.perf_counter() - w0
     clk = clocks.summary(t_start, t_end)
-    clocks.stop()
+    clocks2 = clocks          # keeps sampling through the secondary arms; stopped at the end
 
     if world > 1:
         t = torch.tensor([ms, e2e_s, attn_b2b_ms], dtype=torch.float64, device=dev)
@@ -656,8 +918,64 @@ def _main(out):
         "pdl": not args.no_pdl,
         "gpu_launches": int(launches), "roofline": roofline,
         "host_issue_ms_per_step": host_ms, "tick_ms_alone": tick_ms,
+        "ms_per_step_no_tick": ms_no_tick,
+        "metric_note": "`value` is the step rate of the decode HOT PATH (a1-a7 x layers + LTR "
+                       "tick; the cuBLAS GEMMs, embedding, lm_head and sampler are not executed): "
+                       "batch / time of that kernel chain.  `with_gemms` is the same step with the "
+                       "projections in it, and `trace` is the reference's own metric (output "
+                       "tokens/s and p50 request latency of the whole engine on the trace).",
     }
-    if args.with_gemms and world == 1:
+    if world > 1:
+        line["tp_parity"] = tp_parity
+        if args.tp_exchange != "fused":
+            line["tp_parity"] = "n/a (NCCL all_reduce)"
+    extras = world == 1 and not args.no_extras
+
+    def budget_left():
+        return args.extras_budget_s - (time.time() - t_run0)
+
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), file=out, flush=True)
+
+    if rank == 0:
+        # a driver-side timeout must not lose the measurements already taken
+        import signal
+
+        def on_term(signum, frame):
+            line["terminated_early"] = f"signal {signum} after {time.time() - t_run0:.0f} s"
+            emit()
+            os._exit(0)
+
+        signal.signal(signal.SIGTERM, on_term)
+    ref_cuda = load_ref_cuda() if extras else None
+    if extras and ref_cuda is not None:
+        # the reference's own CUDA kernels (sm_100a build) on the same step, pools and inputs
+        rhp = DecodeHotPath(shape, num_blocks, args.batch, dev, seed=rank, C=ref_cuda)
+        for _ in range(3):
+            rhp.step(devin["hidden"], devin["positions"], devin["slot_mapping"],
+                     devin["block_tables"], devin["context_lens"], max_ctx)
+        barrier()
+        r0 = time.time()
+        rms = time_step_graph(rhp, devin, max_ctx, args.steps)
+        r_attn = time_attention_b2b(rhp, devin, max_ctx, args.batch, args.steps)
+        r1 = time.time()
+        line["ref_cuda"] = {
+            "what": "the same decode step (same call order, shapes, inputs, CUDA-graph replay, no "
+                    "tick) through the reference's CUDA kernels recompiled unmodified for sm_100a "
+                    "(oracle/_ref/ref_cuda_C)",
+            "ms_per_step": rms, "tokens_per_s": args.batch / (rms * 1e-3),
+            "attention_launch_ms": r_attn,
+            "attention_roofline_frac": abytes / (r_attn * 1e-3) / 1e9 / peak,
+            "ours_ms_per_step_no_tick": ms_no_tick,
+            "speedup_ours_vs_ref_cuda": (rms / ms_no_tick) if ms_no_tick else None,
+            "attention_speedup": r_attn / attn_b2b_ms,
+            "clocks": clocks2.summary(r0, r1)}
+        del rhp
+        torch.cuda.empty_cache()
+    elif extras:
+        line["ref_cuda"] = {"unavailable": "oracle/_ref/ref_cuda_C not built"}
+    if (args.with_gemms or extras) and world == 1:
         # context, not the metric: the same step with the dense projections (library code) in it
         hp.enable_gemms()
         g2, out2 = hp.capture(devin["hidden"], devin["positions"], devin["slot_mapping"],
@@ -684,8 +1002,47 @@ def _main(out):
                                                         args.cpu_sample_batch)
         line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": kind,
                                 "sample": desc, "ms_per_step": cms}
-    if rank == 0:
-        print(json.dumps(line), file=out, flush=True)
+    # ---- N=8: the north-star multi-GPU config (Llama-2-70B, TP8) as a second record ----------
+    if world == 8 and args.model != "llama-2-70b" and not args.no_extras and use_graph:
+        line["config_70b"] = measure_70b(args, dev, rank, world, peak)
+    # ---- N=1: the other single-GPU configs, then the engine-level trace ----------------------
+    if extras:
+        del hp, graph, graph_out, tick
+        hp = graph = graph_out = tick = None
+        torch.cuda.empty_cache()
+        line["models"] = {}
+        for name in ("llama-3-8b", "llama-3-8b-fp8kv"):
+            if name == args.model or budget_left() < 240:
+                continue
+            line["models"][name] = step_pair(name, args.batch, args.steps, dev, ref_cuda, peak,
+                                             clocks2, layers=args.layers)
+        torch.cuda.empty_cache()
+        if args.trace != "off":
+            tr = {"workload": f"{args.trace_model} (dummy weights re-drawn N(0,0.02), fp16) + "
+                              f"OPT-125M predictor, {args.trace_prompts} requests at t=0 of the "
+                              "synthetic ShareGPT trace (BASELINE.md section 4), schedule "
+                              f"\"opt-xxx-synthetic((-1,-1,{args.trace_stop}),)\", "
+                              "--enable-chunked-prefill --enforce-eager, 768-token / 256-seq "
+                              "budget, block 16, greedy, ignore_eos; ordering scores = the "
+                              "trace's -log(len)+noise (tau 0.52) in both arms, the predictor "
+                              "still runs and is timed; unmodified reference engine "
+                              "(oracle/_ref/vllm_py) through LLMEngine.step()",
+                  "metric": "output tokens/s and p50 request latency "
+                            "(benchmark_throughput_original.py:436-442)"}
+            arms = [("ours", "b200")] + ([("ref_cuda", "ref_cuda")] if args.trace == "both" else [])
+            for label, arm in arms:
+                left = budget_left()
+                if left < 90:
+                    tr[label] = {"skipped": f"time budget ({args.extras_budget_s:.0f} s) spent"}
+                    continue
+                tr[label] = run_trace_arm(arm, args, clocks2, min(left, 420.0))
+            if "tokens_per_s" in tr.get("ours", {}) and "tokens_per_s" in tr.get("ref_cuda", {}):
+                tr["tokens_per_s_ratio"] = tr["ours"]["tokens_per_s"] / tr["ref_cuda"]["tokens_per_s"]
+                tr["p50_latency_ratio"] = tr["ours"]["p50_latency_s"] / tr["ref_cuda"]["p50_latency_s"]
+            line["trace"] = tr
+    clocks2.stop()
+    line["bench_wall_s"] = time.time() - t_run0
+    emit()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

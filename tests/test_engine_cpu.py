@@ -81,5 +81,4 @@ def test_install_engine_reads_the_reference_predictor_config(env, monkeypatch):
                                     prefill_predictor_model_config=cfg))
     done = integration.install_engine(eng, scheduler=False, prefill=False)
     assert sched.aux_model == "B200AUX" and done["predictor"].startswith("B200AuxModel")
-    assert seen == {"path": "/ckpt", "tokenizer": "/tok", "max_length": 1536,
-                    "max_batch_prompts": 128}
+    assert seen == {"path": "/ckpt", "tokenizer": "/tok", "max_length": 1536}

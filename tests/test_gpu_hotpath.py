@@ -1,4 +1,4 @@
-"""The decode step as a whole (vllm_ltr_b200/hotpath.py: the per-layer op sequence of
+"""The decode step as a whole (tools/hotpath.py: the per-layer op sequence of
 llama.py:215-238 through the vllm._C mirror): against the oracle driven through the same sequence,
 and the launch modes (programmatic dependent launch on/off, CUDA-graph replay) against each other,
 which must agree bit for bit - they run the same kernels on the same data."""
@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from bench import OraclePort, build_inputs, trace_contexts
-from vllm_ltr_b200.hotpath import SHAPES, DecodeHotPath, ModelShape
+from hotpath import SHAPES, DecodeHotPath, ModelShape
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -91,6 +91,21 @@ def test_forward_matches_oracle(P, kind, layers, dtype):
     assert kendall_tau(got[:, 0].tolist(), want[:, 0].tolist()) >= (0.99 if dtype == torch.float16 else 0.85)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention_tile_edges(P, dtype):
+    """Prompt lengths around the 64-row query / 64-key tile edges of the tensor-core attention
+    kernel (and 1-token prompts), in one varlen batch."""
+    cfg, sd = O.random_opt("125m", seed=3, vocab=1500, max_pos=1024, layers=2)
+    g = torch.Generator().manual_seed(17)
+    lens = [1, 2, 15, 16, 17, 63, 64, 65, 127, 128, 129, 191, 192, 193, 255, 256, 257, 500, 1, 1024]
+    prompts = [torch.randint(3, 1500, (L,), generator=g).tolist() for L in lens]
+    got = P.OPTPredictor(cfg, sd, device=DEV, dtype=dtype).logits(prompts).cpu()
+    want = O.opt_logits(cfg, sd, prompts)
+    tol = 2e-2 if dtype == torch.float16 else 1e-1
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= tol, (got - want).abs().max().item()
+
+
 def test_forward_batching_is_invisible(P):
     """Scores do not depend on how prompts are packed into forwards (the reference's aux
     scheduler packs <= 2048 tokens / <= 256 prompts per step)."""
@@ -98,7 +113,8 @@ def test_forward_batching_is_invisible(P):
     prompts = _prompts(40, 700, 1000, 9)
     a = P.OPTPredictor(cfg, sd, device=DEV, max_batch_tokens=2048).logits(prompts)
     b = P.OPTPredictor(cfg, sd, device=DEV, max_batch_tokens=1).logits(prompts)   # one by one
-    assert torch.equal(a, b)
+    c = P.OPTPredictor(cfg, sd, device=DEV).logits(prompts)       # default: one 16k-token batch
+    assert torch.equal(a, b) and torch.equal(a, c)
     long = [[3 + (i * 7) % 990 for i in range(2048)]]                              # max_length
     c = P.OPTPredictor(cfg, sd, device=DEV).logits(long).cpu()
     assert (c - O.opt_logits(cfg, sd, long)).abs().max().item() <= 2e-2

@@ -1,4 +1,4 @@
-"""CPU: the host-side call sequence of vllm_ltr_b200.hotpath.DecodeHotPath driven through the
+"""CPU: the host-side call sequence of tools/hotpath.py DecodeHotPath driven through the
 oracle dressed as a vllm._C module (bench.OraclePort) - the same wiring the benchmark's reference
 arm uses with the reference's CPU kernels.  Checks the plumbing (buffers, views, optional
 projections), not kernels."""
@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from bench import OraclePort, attention_bytes, build_inputs, step_bytes, trace_contexts
-from vllm_ltr_b200.hotpath import SHAPES, DecodeHotPath, ModelShape
+from hotpath import SHAPES, DecodeHotPath, ModelShape
 
 
 def _tiny():

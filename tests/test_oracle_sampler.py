@@ -92,3 +92,14 @@ def test_b200_sampler_host_logic_against_reference(monkeypatch):
     md_bad = SamplingMetadata([([0], bad)], {0: SequenceData([1])}, [], torch.arange(1), cat)
     with pytest.raises(NotImplementedError, match="top_p"):
         sampler_mod.B200Sampler()(logits[:1].clone(), md_bad)
+    # with the engine's own Sampler behind it, such a step is handed over whole
+    calls = []
+
+    class Ref(torch.nn.Module):
+        def forward(self, lg, smd_, pred_scores=None, aux_model_scores=None):
+            calls.append(lg.shape)
+            return "REFERENCE OUTPUT"
+
+    s2 = sampler_mod.B200Sampler(reference=Ref())
+    assert s2(logits[:1].clone(), md_bad) == "REFERENCE OUTPUT"
+    assert s2.reference_steps == 1 and calls == [logits[:1].shape]

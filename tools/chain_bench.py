@@ -17,6 +17,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tools"))
 from bench import build_inputs, trace_contexts  # noqa: E402
 
 DEV = "cuda:0"
@@ -49,7 +50,7 @@ def main():
     args = ap.parse_args()
     from vllm_ltr_b200 import _C
     from vllm_ltr_b200._lib import tune
-    from vllm_ltr_b200.hotpath import SHAPES, DecodeHotPath, ModelShape, forward_decode
+    from hotpath import SHAPES, DecodeHotPath, ModelShape, forward_decode
     peak = 6534.5
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

@@ -19,15 +19,24 @@ ops in scope:
     LlamaModel.forward          llama.py:271-303: final norm -> ops.fused_add_rms_norm
 
 The GEMM outputs (qkv, o_proj, gate_up, down_proj) are stand-in buffers owned by the caller; the
-ops read and write them in place exactly as the reference layers do.  Everything goes through
-``vllm_ltr_b200._C`` (the drop-in ``vllm._C`` surface) - there is no other code path.
+ops read and write them in place exactly as the reference layers do.  Everything goes through a
+``vllm._C``-shaped module: ``vllm_ltr_b200._C`` by default, or the reference's own builds
+(oracle/_ref/ref_cuda_C, ref_cpu_C) for the baseline arms.
+
+BENCH / TEST DRIVER (tools/), not product code: the product is the extension surface itself; in
+the engine this call order is the reference's model code.
 """
 from dataclasses import dataclass
 from typing import List, Optional
 
 import torch
 
-from . import _C
+
+
+def _default_C():
+    from vllm_ltr_b200 import _C      # loads libvllm_ltr_b200.so; not needed by the reference arms
+    return _C
+
 
 _PARTITION_SIZE = 512  # vllm/attention/ops/paged_attn.py:10
 
@@ -82,9 +91,10 @@ def cos_sin_cache(shape: ModelShape, device) -> torch.Tensor:
 
 def forward_decode(query, key_cache, value_cache, block_tables, context_lens, max_context_len,
                    kv_cache_dtype, num_kv_heads, scale, alibi_slopes, kv_scale, out=None,
-                   scratch=None, C=_C):
+                   scratch=None, C=None):
     """PagedAttention.forward_decode (attention/ops/paged_attn.py:83-161), including the
     reference's v1/v2 choice.  ``out`` / ``scratch`` let a caller reuse buffers across steps."""
+    C = _default_C() if C is None else C
     output = torch.empty_like(query) if out is None else out
     block_size = value_cache.shape[3]
     num_seqs, num_heads, head_size = query.shape
@@ -117,7 +127,7 @@ class DecodeHotPath:
                  layers: Optional[int] = None, C=None):
         # C: the extension module to drive.  Always vllm_ltr_b200._C in the product; bench.py's
         # reference arm passes the reference's own CPU build of vllm._C (same surface) instead.
-        self.C = _C if C is None else C
+        self.C = _default_C() if C is None else C
         self.shape = s = shape
         self.device = device
         self.layers = s.layers if layers is None else layers

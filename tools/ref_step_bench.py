@@ -2,7 +2,7 @@
 """The decode hot-path step with OUR kernels next to the same step with the REFERENCE's CUDA
 kernels (csrc/*.cu recompiled unmodified for sm_100a into oracle/_ref/ref_cuda_C by
 oracle/Makefile) - the "reference CUDA build" target of BASELINE.md section 3.1 at step level.
-Both go through vllm_ltr_b200.hotpath.DecodeHotPath (the call sequence of llama.py:215-238) with
+Both go through tools/hotpath.py DecodeHotPath (the call sequence of llama.py:215-238) with
 the same shapes, pools and inputs; only the extension module behind `vllm._C` differs.
 Development tool (run under gpurun), like tools/op_sweep.py.
 
@@ -45,7 +45,7 @@ def main():
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
     from vllm_ltr_b200 import _C
-    from vllm_ltr_b200.hotpath import SHAPES, DecodeHotPath, ModelShape
+    from hotpath import SHAPES, DecodeHotPath, ModelShape
     ref = load_ref()
     assert ref is not None, "oracle/_ref/ref_cuda_C not built (make -C oracle ref_cuda)"
     rows = []

@@ -23,19 +23,30 @@ int launch_mode_bf16_fp8(Params&, int, int, cudaStream_t);
 int launch_mode_f32_fp8(Params&, int, int, cudaStream_t);
 
 // ---- per-device state: work-queue counters, partition tickets, v1 partial workspace -------------
+// Lifetime rules (a captured CUDA graph bakes these pointers into its launches, and launches on
+// different streams may be in flight together):
+//   * buffers are grow-only and a buffer that has ever been handed to a launch is NEVER freed:
+//     growing allocates a new one and retires the old one (kept alive for graphs that replay it);
+//   * nothing is allocated, and the device is never synchronised, while the calling stream is
+//     being captured: a launch that would need to grow there fails with a clear error (run one
+//     eager call of that shape first - the engine's and DecodeHotPath.capture()'s warm-up does);
+//   * every ticket slot owns its own partial workspace, so up to kTicketSlots v1 launches with
+//     partitions can overlap on different streams without sharing scratch.
 constexpr int kCounterSlots = 64;   // launches that may be in flight on different streams
+constexpr int kTicketSlots = 8;
 struct DevState {
   int* counters = nullptr;   // kCounterSlots x 2 ints, zero between launches (self-resetting)
   unsigned next_slot = 0;
-  int* tickets = nullptr;    // kTicketSlots regions of ticket_cap ints, all zero between launches
-  size_t ticket_cap = 0;
+  int* tickets[kTicketSlots] = {};   // ticket_cap ints each, all zero between launches
+  size_t ticket_cap[kTicketSlots] = {};
+  char* ws[kTicketSlots] = {};       // fp32 partials of v1 launches with partitions
+  size_t ws_bytes[kTicketSlots] = {};
   unsigned next_ticket = 0;
-  char* ws = nullptr;        // grow-only
-  size_t ws_bytes = 0;
 };
-constexpr int kTicketSlots = 8;
 static DevState g_dev[64];
 static std::mutex g_mu;
+constexpr size_t kTicketFloor = 65536;   // 256 sequences x 16 kv heads x 16 passes
+constexpr size_t kWsFloor = (size_t)256 * 32 * 17 * (128 + 2) * sizeof(float);
 
 static int get_state(DevState** out) {
   int dev = 0;
@@ -43,39 +54,67 @@ static int get_state(DevState** out) {
   VLTR_CHECK(dev >= 0 && dev < 64, VLTR_ERR_INVALID, "device index %d out of range", dev);
   DevState* st = &g_dev[dev];
   if (st->counters == nullptr) {
-    VLTR_CUDA(cudaMalloc(&st->counters, sizeof(int) * 2 * kCounterSlots));
-    VLTR_CUDA(cudaMemset(st->counters, 0, sizeof(int) * 2 * kCounterSlots));
+    // everything a launch inside the engine's limits (256 sequences, 32 heads of size 128, 17
+    // partitions) can need is allocated here, once, for every slot: ~0.6 GB per device, and no
+    // later call - eager, captured or replayed - ever has to grow
+    int* c = nullptr;
+    VLTR_CUDA(cudaMalloc(&c, sizeof(int) * 2 * kCounterSlots));
+    VLTR_CUDA(cudaMemset(c, 0, sizeof(int) * 2 * kCounterSlots));
+    for (int slot = 0; slot < kTicketSlots; ++slot) {
+      VLTR_CUDA(cudaMalloc(&st->tickets[slot], sizeof(int) * kTicketFloor));
+      VLTR_CUDA(cudaMemset(st->tickets[slot], 0, sizeof(int) * kTicketFloor));
+      st->ticket_cap[slot] = kTicketFloor;
+      VLTR_CUDA(cudaMalloc(&st->ws[slot], kWsFloor));
+      st->ws_bytes[slot] = kWsFloor;
+    }
+    VLTR_CUDA(cudaDeviceSynchronize());
+    st->counters = c;
   }
   *out = st;
   return VLTR_OK;
 }
 
-// grow-only buffers; growing frees the old one after the device drains (first calls only)
-static int ensure_ws(DevState* st, size_t bytes) {
-  if (st->ws_bytes >= bytes) return VLTR_OK;
-  if (st->ws != nullptr) {
-    VLTR_CUDA(cudaDeviceSynchronize());
-    VLTR_CUDA(cudaFree(st->ws));
-    st->ws = nullptr;
-    st->ws_bytes = 0;
-  }
-  size_t cap = bytes + bytes / 2;
-  VLTR_CUDA(cudaMalloc(&st->ws, cap));
-  st->ws_bytes = cap;
+static int capturing(cudaStream_t stream, bool* yes) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  VLTR_CUDA(cudaStreamIsCapturing(stream, &cs));
+  *yes = cs != cudaStreamCaptureStatusNone;
   return VLTR_OK;
 }
-static int ensure_tickets(DevState* st, size_t n) {
-  if (st->ticket_cap >= n) return VLTR_OK;
-  if (st->tickets != nullptr) {
-    VLTR_CUDA(cudaDeviceSynchronize());
-    VLTR_CUDA(cudaFree(st->tickets));
-    st->tickets = nullptr;
-    st->ticket_cap = 0;
-  }
-  size_t cap = n < 4096 ? 4096 : n + n / 2;
-  VLTR_CUDA(cudaMalloc(&st->tickets, sizeof(int) * cap * kTicketSlots));
-  VLTR_CUDA(cudaMemset(st->tickets, 0, sizeof(int) * cap * kTicketSlots));
-  st->ticket_cap = cap;
+
+static int ensure_ws(DevState* st, int slot, size_t bytes, cudaStream_t stream) {
+  if (st->ws_bytes[slot] >= bytes) return VLTR_OK;
+  bool cap = false;
+  int rc = capturing(stream, &cap);
+  if (rc) return rc;
+  VLTR_CHECK(!cap, VLTR_ERR_INVALID,
+             "paged_attention_v1: the partial workspace must grow (%zu bytes) while the stream is "
+             "being captured; run one eager call of this shape before capturing", bytes);
+  // beyond the pre-allocated floor (larger batches / more heads than the engine's limits): the
+  // old buffer is retired alive, never freed
+  const size_t want = bytes + bytes / 2;
+  char* fresh = nullptr;
+  VLTR_CUDA(cudaMalloc(&fresh, want));
+  st->ws[slot] = fresh;
+  st->ws_bytes[slot] = want;
+  return VLTR_OK;
+}
+static int ensure_tickets(DevState* st, int slot, size_t n, cudaStream_t stream) {
+  if (st->ticket_cap[slot] >= n) return VLTR_OK;
+  bool cap = false;
+  int rc = capturing(stream, &cap);
+  if (rc) return rc;
+  VLTR_CHECK(!cap, VLTR_ERR_INVALID,
+             "paged_attention: the ticket table must grow (%zu entries) while the stream is being "
+             "captured; run one eager call of this shape before capturing", n);
+  const size_t want = n + n / 2;
+  int* fresh = nullptr;
+  VLTR_CUDA(cudaMalloc(&fresh, sizeof(int) * want));
+  // plain (legacy-stream) memset: ordered before any later launch on a blocking stream, and
+  // followed by a synchronise for non-blocking ones - growth is a first-calls-only event
+  VLTR_CUDA(cudaMemset(fresh, 0, sizeof(int) * want));
+  VLTR_CUDA(cudaDeviceSynchronize());
+  st->tickets[slot] = fresh;       // the previous table stays allocated (replayed graphs use it)
+  st->ticket_cap[slot] = want;
   return VLTR_OK;
 }
 
@@ -186,26 +225,27 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     p.part_blocks_cap = pb;
     p.always_partial = 0;
     p.tmp_is_f32 = 1;
-    if (p.n_part > 1) {
+  }
+  int slot = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    slot = (int)(st->next_ticket++ % kTicketSlots);
+    if (!v2 && p.n_part > 1) {
       const size_t n = (size_t)num_seqs * num_heads * p.n_part;
       const size_t bytes = n * sizeof(float) * 2 + n * head_size * sizeof(float);
-      std::lock_guard<std::mutex> lk(g_mu);
-      int rc = ensure_ws(st, bytes);
+      int rc = ensure_ws(st, slot, bytes, stream);
       if (rc) return rc;
-      p.exp_sums = reinterpret_cast<float*>(st->ws);
+      p.exp_sums = reinterpret_cast<float*>(st->ws[slot]);
       p.max_logits = p.exp_sums + n;
       p.tmp_out = p.max_logits + n;
     }
-  }
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
     const size_t ngroups = (size_t)num_seqs * num_kv_heads * 16;   // passes <= 16 for any sane G
-    int rc = ensure_tickets(st, ngroups);
+    int rc = ensure_tickets(st, slot, ngroups, stream);
     if (rc) return rc;
-    p.tickets = st->tickets + (size_t)(st->next_ticket++ % kTicketSlots) * st->ticket_cap;
+    p.tickets = st->tickets[slot];
     p.counters = st->counters + 2 * (st->next_slot++ % kCounterSlots);
   }
-  VLTR_CHECK((long long)num_seqs * num_kv_heads * p.passes <= (long long)st->ticket_cap,
+  VLTR_CHECK((long long)num_seqs * num_kv_heads * p.passes <= (long long)st->ticket_cap[slot],
              VLTR_ERR_INVALID, "paged_attention: too many head groups");
 
   if (!kv_fp8) {

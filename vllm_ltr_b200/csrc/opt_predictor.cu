@@ -324,109 +324,225 @@ __global__ void __launch_bounds__(128)
 }
 
 // causal varlen attention, head size 64.  qkv [M, 3H] (q | k | v), out [M, H].
-// grid (q tiles of 128 rows over max_len, heads, prompts); one thread per query row.
-__device__ __forceinline__ float fma_mixed(__half a, __half b, float c) {
-  float r;
-  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
-  return r;
-}
-__device__ __forceinline__ float fma_mixed(__nv_bfloat16 a, __nv_bfloat16 b, float c) {
-  float r;
-  asm("fma.rn.f32.bf16 %0, %1, %2, %3;"
-      : "=f"(r)
-      : "h"(__bfloat16_as_ushort(a)), "h"(__bfloat16_as_ushort(b)), "f"(c));
-  return r;
-}
+//
+// Flash-style tile kernel on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate):
+// grid (query tiles of 64 rows over max_len - heaviest first, heads, prompts), 4 warps x 16 query
+// rows.  K/V tiles of 64 keys x 64 dims are staged by cp.async into a double-buffered, XOR-
+// swizzled shared-memory ring; Q.K^T takes its B fragments with ldmatrix, P.V with
+// ldmatrix.trans; the online softmax lives in registers (row statistics reduced across the 4
+// lanes that share a row), P is rounded to T before P.V as flash-attn does (the reference's
+// prefill path, attention/backends/flash_attn.py:217-235).  The contraction is tiny next to the
+// dense layers (head size 64), so it stays on mma.sync rather than paying a TMEM round trip.
+constexpr int kAttnRows = 64, kAttnKeys = 64, kHD = 64, kAttnThreads = 128;
 
-constexpr int kAttnRows = 128, kAttnKeys = 64, kHD = 64;
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;          // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&d)[4], const uint32_t (&a)[4],
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4],
+                                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// tile row r (128 bytes = 8 chunks of 16 B), chunk c: XOR swizzle keeps ldmatrix conflict-free
+__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <typename T>
-__global__ void __launch_bounds__(kAttnRows)
+__global__ void __launch_bounds__(kAttnThreads)
     attention_kernel(const T* __restrict__ qkv, T* __restrict__ out,
                      const int32_t* __restrict__ cu_seqlens, int H, float scale) {
-  __shared__ __align__(16) T sk[kAttnKeys][kHD];
-  __shared__ __align__(16) T sv[kAttnKeys][kHD];
+  // [Q | K0 | V0 | K1 | V1], each 64 rows x 128 B
+  __shared__ __align__(128) unsigned char smem[5 * kAttnKeys * 128];
   pdl_wait();
   pdl_trigger();
   const int prompt = blockIdx.z, head = blockIdx.y;
   const int t0 = cu_seqlens[prompt], len = cu_seqlens[prompt + 1] - t0;
-  const int q0 = blockIdx.x * kAttnRows;
+  const int q0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * kAttnRows;   // long (late) tiles first
   if (q0 >= len) return;
-  const int qi = q0 + threadIdx.x;            // my query position inside the prompt
-  const bool live = qi < len;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ld = 3 * (int64_t)H;
-  alignas(16) T q[kHD];
-  if (live) {
-    const T* qp = qkv + (t0 + qi) * ld + head * kHD;
-#pragma unroll
-    for (int i = 0; i < kHD; i += 8)
-      *reinterpret_cast<uint4*>(&q[i]) = *reinterpret_cast<const uint4*>(qp + i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < kHD; ++i) q[i] = ST<T>::from_f(0.f);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sq = sbase;
+  const T* base = qkv + (int64_t)t0 * ld + head * kHD;
+
+  // ---- stage Q (group 0) and the first K/V tile (group 1) --------------------------------------
+  for (int i = tid; i < kAttnRows * 8; i += kAttnThreads) {
+    const int r = i >> 3, c = i & 7;
+    cp_async_16(sq + tile_off(r, c), base + (int64_t)min(q0 + r, len - 1) * ld + c * 8, q0 + r < len);
   }
-  float o[kHD];
+  cp_async_commit();
+  const int kend = min(len, q0 + kAttnRows);          // causal: keys up to this tile's last query
+  const int ntiles = (kend + kAttnKeys - 1) / kAttnKeys;
+  auto stage_kv = [&](int kt, int buf) {
+    const uint32_t sk = sbase + (1 + 2 * buf) * (kAttnKeys * 128), sv = sk + kAttnKeys * 128;
+    const int k0 = kt * kAttnKeys;
+    for (int i = tid; i < kAttnKeys * 8; i += kAttnThreads) {
+      const int r = i >> 3, c = i & 7;
+      const bool ok = k0 + r < len;
+      const T* kp = base + (int64_t)min(k0 + r, len - 1) * ld + H + c * 8;
+      cp_async_16(sk + tile_off(r, c), kp, ok);
+      cp_async_16(sv + tile_off(r, c), kp + H, ok);      // rows past the prompt are zero-filled
+    }
+  };
+  stage_kv(0, 0);
+  cp_async_commit();
+
+  // ---- Q fragments: 16 rows x 64 dims per warp = 4 k-steps of A (m16 x k16) --------------------
+  cp_async_wait<1>();
+  __syncthreads();
+  uint32_t qf[4][4];
+  {
+    const int mi = lane >> 3, r = lane & 7;
+    const int row = warp * 16 + (mi & 1) * 8 + r;
 #pragma unroll
-  for (int i = 0; i < kHD; ++i) o[i] = 0.f;
-  float m = -INFINITY, l = 0.f;
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(sq + tile_off(row, ks * 2 + (mi >> 1)), qf[ks]);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g + 8 of this warp
   const float sl2 = scale * 1.4426950408889634f;
-  const int kmax = min(len, q0 + kAttnRows);   // causal: keys up to the last query of this tile
-  for (int k0 = 0; k0 < kmax; k0 += kAttnKeys) {
+  const int g = lane >> 2, tq = lane & 3;
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;        // query positions in the prompt
+
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ntiles) stage_kv(kt + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    // stage K and V rows k0 .. k0+63 of this head (64 rows x 128 B each)
-    for (int i = threadIdx.x; i < kAttnKeys * (kHD / 8); i += kAttnRows) {
-      const int r = i / (kHD / 8), c = (i % (kHD / 8)) * 8;
-      uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (k0 + r < len) {
-        const T* kp = qkv + (t0 + k0 + r) * ld + H + head * kHD + c;
-        kk = *reinterpret_cast<const uint4*>(kp);
-        vv = *reinterpret_cast<const uint4*>(kp + H);
-      }
-      *reinterpret_cast<uint4*>(&sk[r][c]) = kk;
-      *reinterpret_cast<uint4*>(&sv[r][c]) = vv;
+    const uint32_t sk = sbase + (1 + 2 * buf) * (kAttnKeys * 128), sv = sk + kAttnKeys * 128;
+    const int k0 = kt * kAttnKeys;
+    // ---- S = Q . K^T  (16 x 64 per warp) --------------------------------------------------------
+    float sc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[n][e] = 0.f;
+      const int krow = n * 8 + (lane & 7), mi = lane >> 3;
+      uint32_t b[4];
+      ldsm_x4(sk + tile_off(krow, mi), b);           // dims 0..31: k-steps 0 and 1
+      mma_16816<T>(sc[n], qf[0], b[0], b[1]);
+      mma_16816<T>(sc[n], qf[1], b[2], b[3]);
+      ldsm_x4(sk + tile_off(krow, 4 + mi), b);       // dims 32..63: k-steps 2 and 3
+      mma_16816<T>(sc[n], qf[2], b[0], b[1]);
+      mma_16816<T>(sc[n], qf[3], b[2], b[3]);
     }
-    __syncthreads();
-    const int nkeys = min(kAttnKeys, kmax - k0);
-    for (int j = 0; j < nkeys; ++j) {
-      if (k0 + j > qi) break;                  // causal mask (also retires rows past the prompt)
-      float s = 0.f;
+    // ---- scale, causal mask (diagonal tile only), online softmax ------------------------------
+    const bool diag = k0 + kAttnKeys > q0 + warp * 16;      // some key of the tile is past a row
+    float mx0 = m0, mx1 = m1;
 #pragma unroll
-      for (int i = 0; i < kHD; i += 8) {
-        alignas(16) T kk[8];
-        *reinterpret_cast<uint4*>(kk) = *reinterpret_cast<const uint4*>(&sk[j][i]);
+    for (int n = 0; n < 8; ++n) {
+      const int key = k0 + n * 8 + tq * 2;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s = fma_mixed(q[i + e], kk[e], s);
+      for (int e = 0; e < 4; ++e) {
+        float v = sc[n][e] * sl2;
+        if (diag && key + (e & 1) > ((e & 2) ? row1 : row0)) v = -INFINITY;
+        sc[n][e] = v;
       }
-      s *= sl2;
-      const float mn = fmaxf(m, s);
-      if (mn > m) {
-        const float a = exp2f(m - mn);
-        l *= a;
+      mx0 = fmaxf(mx0, fmaxf(sc[n][0], sc[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[n][2], sc[n][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    // key 0 is visible to every row, so mx is finite from the first tile on
+    const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);
+    m0 = mx0;
+    m1 = mx1;
+    l0 *= a0;
+    l1 *= a1;
 #pragma unroll
-        for (int i = 0; i < kHD; ++i) o[i] *= a;
-        m = mn;
-      }
-      const T ph = ST<T>::from_f(exp2f(s - m));   // P is rounded to T before P.V, as flash-attn does
-      l += ST<T>::to_f(ph);
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= a0;
+      o[n][1] *= a0;
+      o[n][2] *= a1;
+      o[n][3] *= a1;
+    }
+    uint32_t pf[4][4];        // P as A fragments: k-step j covers keys 16j .. 16j+15
 #pragma unroll
-      for (int i = 0; i < kHD; i += 8) {
-        alignas(16) T vv[8];
-        *reinterpret_cast<uint4*>(vv) = *reinterpret_cast<const uint4*>(&sv[j][i]);
+    for (int n = 0; n < 8; ++n) {
+      const float p0 = exp2f(sc[n][0] - m0), p1 = exp2f(sc[n][1] - m0);
+      const float p2 = exp2f(sc[n][2] - m1), p3 = exp2f(sc[n][3] - m1);
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      pf[n >> 1][(n & 1) * 2 + 0] = pack2<T>(p0, p1);
+      pf[n >> 1][(n & 1) * 2 + 1] = pack2<T>(p2, p3);
+    }
+    // ---- O += P . V ---------------------------------------------------------------------------
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[i + e] = fma_mixed(ph, vv[e], o[i + e]);
+    for (int j = 0; j < 4; ++j) {
+      const int mi = lane >> 3, r = lane & 7;
+      const int vrow = j * 16 + (mi & 1) * 8 + r;
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ldsm_x4_t(sv + tile_off(vrow, np * 2 + (mi >> 1)), b);
+        mma_16816<T>(o[np * 2], pf[j], b[0], b[1]);
+        mma_16816<T>(o[np * 2 + 1], pf[j], b[2], b[3]);
       }
     }
+    __syncthreads();          // everyone is done with `buf` before it is refilled
   }
-  if (live) {
-    const float inv = 1.f / l;
-    T* op = out + (int64_t)(t0 + qi) * H + head * kHD;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  T* op = out + (int64_t)t0 * H + head * kHD + tq * 2;
 #pragma unroll
-    for (int i = 0; i < kHD; i += 8) {
-      alignas(16) T r[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] = ST<T>::from_f(o[i + e] * inv);
-      *reinterpret_cast<uint4*>(op + i) = *reinterpret_cast<uint4*>(r);
-    }
+  for (int n = 0; n < 8; ++n) {
+    if (row0 < len)
+      *reinterpret_cast<uint32_t*>(op + (int64_t)row0 * H + n * 8) = pack2<T>(o[n][0] * i0, o[n][1] * i0);
+    if (row1 < len)
+      *reinterpret_cast<uint32_t*>(op + (int64_t)row1 * H + n * 8) = pack2<T>(o[n][2] * i1, o[n][3] * i1);
   }
 }
 
@@ -584,7 +700,7 @@ static int forward_t(const Model& mdl, const int32_t* ids, const int32_t* positi
       a_in = x;
     }
     if ((rc = gemm(a_in, w.qkv_w[L], qkv, w.qkv_b[L], nullptr, M, 3 * H, H, 0, dt, s))) return rc;
-    launch(attention_kernel<T>, dim3(agrid), dim3(kAttnRows), 0, s, qkv, att, cu_seqlens, H, scale);
+    launch(attention_kernel<T>, dim3(agrid), dim3(kAttnThreads), 0, s, qkv, att, cu_seqlens, H, scale);
     VLTR_LAUNCH_CHECK("opt_attention");
     if (c.do_layer_norm_before) {
       // h = h + out_proj(att)

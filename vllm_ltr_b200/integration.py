@@ -11,7 +11,7 @@ Each piece is optional and reported; pieces whose preconditions do not hold (sch
 "opt*", no predictor configured, Ray workers instead of an in-process driver worker) are skipped
 with the reason, never silently replaced by something else.
 """
-from typing import Dict
+from typing import Dict, Optional
 
 
 def _release_aux_engine(aux) -> None:
@@ -32,7 +32,7 @@ def _release_aux_engine(aux) -> None:
 
 def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap: bool = True,
                    decode_inputs: bool = True, sampler: bool = True, prefill: bool = True,
-                   sampler_seed: int = 0,
+                   sampler_seed: Optional[int] = None,
                    release_reference_predictor: bool = True) -> Dict[str, str]:
     done: Dict[str, str] = {}
     sched = getattr(engine, "scheduler", None)
@@ -57,8 +57,7 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
             from .predictor import B200AuxModel
             old = sched.aux_model
             sched.aux_model = B200AuxModel.from_pretrained(
-                m.path, tokenizer=m.pred_model, max_length=m.max_length,
-                max_batch_prompts=min(int(getattr(m, "max_batch_size", 256) or 256), 256))
+                m.path, tokenizer=m.pred_model, max_length=m.max_length)
             if release_reference_predictor:
                 _release_aux_engine(old)
             done["predictor"] = "B200AuxModel (tcgen05 OPT forward) behind scheduler.aux_model"
@@ -89,16 +88,19 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
             model = getattr(runner, "model", None)
             if model is not None and hasattr(model, "sampler"):
                 from .sampler import B200Sampler
-                model.sampler = B200Sampler(seed=sampler_seed)
-                done["sampler"] = ("B200Sampler (greedy / temperature requests; others raise "
-                                   "NotImplementedError)")
+                old = model.sampler
+                if isinstance(old, B200Sampler):
+                    old = old.reference
+                model.sampler = B200Sampler(seed=sampler_seed, reference=old)
+                done["sampler"] = ("B200Sampler (greedy / temperature requests; a step with any "
+                                   "other request goes to the engine's own Sampler)")
             else:
                 done["sampler"] = "skipped: model has no .sampler attribute"
 
     if prefill:
         try:
             from . import prefix_prefill
-            prefix_prefill.install()
+            prefix_prefill.install(engine_path=True)
             done["prefill"] = "context_attention_fwd (Triton) -> vltr_context_attention_fwd"
         except ImportError as e:      # the reference's attention package is not importable here
             done["prefill"] = f"skipped: {e}"

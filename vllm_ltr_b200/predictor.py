@@ -119,8 +119,8 @@ class OPTPredictor:
     (opt.py:411-444): ``model.decoder.layers.N.self_attn.q_proj.weight`` ... ``score.weight``."""
 
     def __init__(self, config: Dict, state_dict: Dict[str, torch.Tensor], device="cuda:0",
-                 dtype: torch.dtype = torch.float16, max_batch_tokens: int = 2048,
-                 max_batch_prompts: int = 256):
+                 dtype: torch.dtype = torch.float16, max_batch_tokens: int = 16384,
+                 max_batch_prompts: int = 2048):
         if not torch.cuda.is_available():
             raise RuntimeError("vllm_ltr_b200 predictor needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -229,8 +229,11 @@ class OPTPredictor:
 
     def logits(self, prompts: Sequence[Sequence[int]]) -> torch.Tensor:
         """[len(prompts), num_labels] float32 logits (values already rounded to the model dtype),
-        on the device.  Prompts are batched like the reference's aux scheduler does
-        (<= max(max_model_len, 2048) tokens and <= 256 prompts per forward, config.py:586)."""
+        on the device.  Prompts are packed into varlen batches of <= max_batch_tokens tokens and
+        <= max_batch_prompts prompts per forward.  (The reference's aux scheduler batches
+        <= max(max_model_len, 2048) tokens and <= 256 prompts per step, config.py:586; a prompt's
+        score does not depend on what it is batched with, and larger batches fill the dense-layer
+        grids: 128-row tiles x 148 SMs.)"""
         out = torch.empty(len(prompts), self.num_labels, dtype=torch.float32, device=self.device)
         i = 0
         while i < len(prompts):

@@ -64,7 +64,23 @@ def context_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: 
             1 if cache_has_new_tokens else 0, stream_of(q)))
 
 
-def install() -> None:
-    """Point the reference's PagedAttention.forward_prefix at this implementation."""
+def install(engine_path: bool = True) -> None:
+    """Point the reference's PagedAttention.forward_prefix at this implementation.
+
+    ``engine_path=True`` (the default): the only caller is ``FlashAttentionImpl.forward``, which
+    has already stored the chunk's k / v with ``write_to_paged_cache`` (flash_attn.py:192) before
+    it reaches ``forward_prefix`` (:240-252) - so the kernel is bound with
+    ``cache_has_new_tokens=True`` and does not scatter them a second time (one launch and one
+    pass over the chunk's cache lines less per layer).  ``engine_path=False`` keeps the
+    stand-alone semantics of the Triton kernel (cache holds only the prefix; used by the unit
+    tests, which call it the way tests/kernels/test_prefix_prefill.py does).
+
+    Numerical note for an fp8 (e5m2) cache: the chunk's own keys / values are read back from the
+    cache, i.e. in their e5m2-rounded form, where the Triton kernel uses the unquantised k / v
+    of the current chunk (and e5m2 values for the prefix).  Decode attention sees the quantised
+    values either way."""
+    import functools
+
     import vllm.attention.ops.paged_attn as pa
-    pa.context_attention_fwd = context_attention_fwd
+    pa.context_attention_fwd = (functools.partial(context_attention_fwd, cache_has_new_tokens=True)
+                                if engine_path else context_attention_fwd)

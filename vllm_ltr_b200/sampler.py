@@ -9,9 +9,11 @@ prompt/output token matrices on the host for penalties nobody asked for
 (sampling_metadata.py:95-200, :207-330).  Here one kernel reads each logits row once.
 
 ``sample_rows``   tensor-level entry (tests, bench): tokens, logprobs, ranks for [rows, vocab] logits.
-``B200Sampler``   drop-in for the engine: ``model.sampler = B200Sampler()``; same ``forward``
-                  signature and ``SamplerOutput``; requests outside the subset raise
-                  ``NotImplementedError`` (there is no silent fallback).
+``B200Sampler``   drop-in for the engine: ``model.sampler = B200Sampler(reference=old_sampler)``;
+                  same ``forward`` signature and ``SamplerOutput``.  A step whose batch contains a
+                  request outside the subset is handed, whole, to the reference ``Sampler`` the
+                  engine was built with (counted in ``.reference_steps``); without one it raises
+                  ``NotImplementedError``.
 """
 import ctypes
 from typing import List, Optional, Tuple
@@ -76,37 +78,52 @@ def sample_rows(logits: torch.Tensor, temperatures: Optional[torch.Tensor] = Non
 
 class B200Sampler(torch.nn.Module):
     """``Sampler.forward(logits, sampling_metadata, pred_scores, aux_model_scores)`` on the fused
-    kernel.  The Philox offset advances by one per call, so steps draw independent noise; pass
-    ``seed`` for reproducible runs (the reference uses torch's global generator)."""
+    kernel.  The Philox offset advances by one per call, so steps draw independent noise.  The
+    default seed is derived from torch's global seed (``torch.initial_seed()``), so
+    ``torch.manual_seed`` / the engine's ``seed`` argument make runs reproducible like they do for
+    the reference (which draws from torch's global generator); pass ``seed`` to pin it."""
 
-    def __init__(self, seed: int = 0):
+    def __init__(self, seed: Optional[int] = None, reference: Optional[torch.nn.Module] = None):
         super().__init__()
-        self.seed = seed
+        self.seed = (torch.initial_seed() & (2 ** 63 - 1)) if seed is None else seed
         self.calls = 0
+        self.reference = reference
+        self.reference_steps = 0
+        self._stage = None           # pinned fp32: temperatures | random flags of one step
 
     @staticmethod
-    def _check(i, sp, sampling_metadata):
+    def _unsupported(i, sp, sampling_metadata) -> Optional[str]:
         from vllm.sampling_params import SamplingType
-        bad = None
         if sp.sampling_type not in (SamplingType.GREEDY, SamplingType.RANDOM):
-            bad = f"sampling_type {sp.sampling_type!r}"
-        elif sp.prompt_logprobs is not None:
-            bad = "prompt_logprobs"
-        elif sp.logprobs is not None and sp.logprobs > 0:
-            bad = "logprobs > 0"
-        elif sp.top_p < 1.0 - _SAMPLING_EPS or sp.top_k != -1 or sp.min_p > _SAMPLING_EPS:
-            bad = "top_p / top_k / min_p"
-        elif (abs(sp.presence_penalty) >= _SAMPLING_EPS or abs(sp.frequency_penalty) >= _SAMPLING_EPS
-              or abs(sp.repetition_penalty - 1.0) >= _SAMPLING_EPS):
-            bad = "presence / frequency / repetition penalty"
-        elif getattr(sp, "min_tokens", 0) > 0:
-            bad = "min_tokens"
-        elif i < sampling_metadata.num_prompts and sp.best_of > 1:
-            bad = "best_of > 1"
-        if bad is not None:
-            raise NotImplementedError(
-                f"vllm_ltr_b200.B200Sampler handles greedy / temperature sampling only; request "
-                f"uses {bad} - keep the reference Sampler for it")
+            return f"sampling_type {sp.sampling_type!r}"
+        if sp.prompt_logprobs is not None:
+            return "prompt_logprobs"
+        if sp.logprobs is not None and sp.logprobs > 0:
+            return "logprobs > 0"
+        if sp.top_p < 1.0 - _SAMPLING_EPS or sp.top_k != -1 or sp.min_p > _SAMPLING_EPS:
+            return "top_p / top_k / min_p"
+        if (abs(sp.presence_penalty) >= _SAMPLING_EPS or abs(sp.frequency_penalty) >= _SAMPLING_EPS
+                or abs(sp.repetition_penalty - 1.0) >= _SAMPLING_EPS):
+            return "presence / frequency / repetition penalty"
+        if getattr(sp, "min_tokens", 0) > 0:
+            return "min_tokens"
+        if getattr(sp, "logits_processors", None):
+            return "logits_processors"
+        if i < sampling_metadata.num_prompts and sp.best_of > 1:
+            return "best_of > 1"
+        return None
+
+    def _staged(self, temps: List[float], rnd: List[int], device):
+        """temperatures / random flags through one pinned buffer and one non-blocking copy."""
+        n = len(temps)
+        if self._stage is None or self._stage.numel() < 2 * n:
+            self._stage = torch.empty(2 * max(n, 1024), dtype=torch.float32)
+            if torch.cuda.is_available():
+                self._stage = self._stage.pin_memory()
+        self._stage[:n] = torch.tensor(temps, dtype=torch.float32)
+        self._stage[n:2 * n] = torch.tensor(rnd, dtype=torch.float32)
+        d = self._stage[:2 * n].to(device, non_blocking=True)   # forward() syncs before returning
+        return d[:n], d[n:].to(torch.uint8)
 
     def forward(self, logits: torch.Tensor, sampling_metadata, pred_scores=None,
                 aux_model_scores=None):
@@ -117,15 +134,25 @@ class B200Sampler(torch.nn.Module):
         temps: List[float] = []
         rnd: List[int] = []
         for i, (seq_ids, sp) in enumerate(sampling_metadata.seq_groups):
-            self._check(i, sp, sampling_metadata)
+            bad = self._unsupported(i, sp, sampling_metadata)
+            if bad is not None:
+                if self.reference is None:
+                    raise NotImplementedError(
+                        f"vllm_ltr_b200.B200Sampler handles greedy / temperature sampling only; "
+                        f"request uses {bad} - construct it with reference=<the engine's Sampler>")
+                self.reference_steps += 1
+                return self.reference(logits, sampling_metadata, pred_scores=pred_scores,
+                                      aux_model_scores=aux_model_scores)
             t = sp.temperature if sp.temperature >= _SAMPLING_EPS else 1.0   # sampling_metadata.py:133-137
             temps += [t] * len(seq_ids)
             rnd += [int(sp.sampling_type == SamplingType.RANDOM)] * len(seq_ids)
         assert len(temps) == logits.shape[0]
         all_unit = all(t == 1.0 for t in temps)
+        td = rd = None
+        if not all_unit or any(rnd):
+            td, rd = self._staged(temps, rnd, logits.device)
         tokens, lps, ranks, _, _ = sample_rows(
-            logits, None if all_unit else torch.tensor(temps, dtype=torch.float32),
-            torch.tensor(rnd, dtype=torch.uint8) if any(rnd) else None,
+            logits, None if all_unit else td, rd if any(rnd) else None,
             seed=self.seed, offset=self.calls)
         self.calls += 1
         packed = torch.stack((tokens.to(torch.float64), lps.to(torch.float64),

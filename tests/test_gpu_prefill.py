@@ -124,3 +124,51 @@ def test_errors(fwd):
     with pytest.raises(RuntimeError, match="max 16"):
         fwd(c32["q"], c32["k"], c32["v"], torch.empty_like(c32["q"]), c32["kc"], c32["vc"],
             c32["bt"], c32["start"], c32["sl"], c32["cl"], 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# side by side with the REFERENCE's own kernel: Triton context_attention_fwd
+# (vllm/attention/ops/prefix_prefill.py:630-755), loaded from the unmodified package shipped to
+# the GPU box (oracle/_ref/vllm_py).  Pins both our kernel and the oracle's restatement to the
+# reference's output on identical inputs.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def triton_fwd():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "vllm_py", "vllm", "attention", "ops",
+                        "prefix_prefill.py")
+    if not os.path.exists(path):
+        path = "/root/reference/vllm/attention/ops/prefix_prefill.py"
+    if not os.path.exists(path):
+        pytest.skip("reference package not shipped (make -C oracle vllm_py)")
+    spec = importlib.util.spec_from_file_location("ref_prefix_prefill", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.context_attention_fwd
+
+
+@pytest.mark.parametrize("heads,G,bs,dtype", [(32, 1, 16, torch.float16), (32, 4, 16, torch.bfloat16),
+                                              (64, 8, 32, torch.float16), (8, 1, 16, torch.bfloat16)])
+def test_against_reference_triton_kernel(fwd, triton_fwd, heads, G, bs, dtype):
+    sub = [1, bs - 1, bs, bs + 1, 17, 100, 333, 2, 64, 128]
+    ctx = [0, 0, 3, bs, 1, 700, 0, 1500, bs - 1, 4 * bs]
+    c = build(heads, G, 128, bs, dtype, sub, ctx, 0.5, 21)
+    theirs = torch.zeros_like(c["q"])
+    triton_fwd(c["q"], c["k"], c["v"], theirs, c["kc"].clone(), c["vc"].clone(), c["bt"],
+               c["start"], c["sl"], c["cl"], c["max_sub"])
+    ours = torch.full_like(c["q"], float("nan"))
+    fwd(c["q"], c["k"], c["v"], ours, c["kc"].clone(), c["vc"].clone(), c["bt"], c["start"],
+        c["sl"], c["cl"], c["max_sub"])
+    ref = K.context_attention(c["q"], c["k"], c["v"], c["kc"], c["vc"], c["bt"], c["start"],
+                              c["sl"], c["cl"], None, "auto")
+    tol = 4e-3 if dtype == torch.bfloat16 else 2e-3
+    e_ours = (ours.float() - ref).abs().max().item()
+    e_theirs = (theirs.float() - ref).abs().max().item()
+    e_pair = (ours.float() - theirs.float()).abs().max().item()
+    print(f"prefill vs oracle: ours {e_ours:.2e}, reference Triton {e_theirs:.2e}; "
+          f"ours vs Triton {e_pair:.2e}")
+    assert e_theirs <= tol, e_theirs          # the oracle restates the reference kernel
+    assert e_ours <= tol, e_ours
+    assert e_pair <= 2 * tol, e_pair

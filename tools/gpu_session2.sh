@@ -1,0 +1,26 @@
+#!/bin/bash
+# round-2 GPU session: full GPU test-suite, prefill bench, predictor sweep, default bench.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+stage() { echo "=== $1 ($(date +%T))" | tee -a $O/session2.log; }
+for s in ${STAGES:-tests prefill bench}; do
+case $s in
+tests) stage "pytest -m gpu"
+  timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  tail -15 $O/pytest_gpu.log;;
+prefill) stage "prefill bench"
+  timeout 600 python tools/prefill_bench.py --json $O/prefill_bench.json > $O/prefill_bench.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  cat $O/prefill_bench.log | tail -20;;
+bench) stage "bench.py default"
+  timeout 1200 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "rc=$?" | tee -a $O/session2.log
+  head -c 6000 $O/bench_default.json; tail -5 $O/bench_default.err;;
+benchref) stage "bench.py --impl reference"
+  timeout 600 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err; echo "rc=$?" | tee -a $O/session2.log
+  head -c 1500 $O/bench_reference.json;;
+trace7b) for arm in b200; do stage "7B trace $arm"
+  timeout 900 python tools/engine_trace.py --arm $arm --model llama-2-7b --num-prompts 10000 --stop-after 1000 --json $O/e_7b_$arm.json > $O/e_7b_$arm.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  grep TRACE $O/e_7b_$arm.log | tail -1 | head -c 1500; done;;
+esac
+done
+stage done

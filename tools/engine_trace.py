@@ -229,7 +229,6 @@ def bind_arm(arm: str) -> None:
     os.environ.setdefault("VLLM_DO_NOT_TRACK", "1")
     os.environ.setdefault("HF_HUB_OFFLINE", "1")
     os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
-    os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
     if arm == "b200":
         import vllm_ltr_b200
         vllm_ltr_b200.install()
@@ -359,7 +358,7 @@ class TimedScores:
 
 def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = False,
               logprobs: Optional[int] = None, temperature: float = 0.0,
-              max_steps: Optional[int] = None) -> dict:
+              max_steps: Optional[int] = None, profile: Optional[tuple] = None) -> dict:
     """The request loop of benchmark_throughput_original.py:251-270 + LLM._run_engine
     (entrypoints/llm.py:221-246), instrumented per step."""
     import torch
@@ -411,12 +410,26 @@ def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = Fals
     sync()
     start = time.perf_counter()
     sched.start_time = time.time()
+    prof = None
     while eng.has_unfinished_requests():
+        if profile is not None and steps == profile[0]:
+            from torch.profiler import ProfilerActivity
+            from torch.profiler import profile as _profile
+            sync()
+            prof = _profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+            prof.__enter__()
+            prof_t0 = time.perf_counter()
         for out in eng.step():
             if out.finished:
                 out.latency = time.perf_counter() - start
                 outputs.append(out)
         steps += 1
+        if prof is not None and steps == profile[0] + profile[1]:
+            sync()
+            wall = time.perf_counter() - prof_t0
+            prof.__exit__(None, None, None)
+            _dump_profile(prof, wall, profile[1], profile[2])
+            prof = None
         if max_steps is not None and steps >= max_steps:
             break
     sync()
@@ -458,6 +471,27 @@ def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = Fals
     return {"summary": res, "detail": detail}
 
 
+def _dump_profile(prof, wall_s, nsteps, path):
+    """Per-kernel device time and the host-side picture of `nsteps` engine steps."""
+    ka = prof.key_averages()
+    dev = []
+    for e in ka:
+        t = getattr(e, "self_device_time_total", 0) or 0
+        if t > 0:
+            dev.append((t, e.count, e.key))
+    dev.sort(reverse=True)
+    busy = sum(t for t, _, _ in dev)
+    with open(path, "w") as f:
+        f.write(f"{nsteps} engine steps, wall {wall_s * 1e3:.1f} ms = {wall_s / nsteps * 1e3:.2f} "
+                f"ms/step; device busy {busy / 1e3:.1f} ms ({100 * busy / 1e6 / wall_s:.0f}% of wall)\n\n")
+        f.write("device time by kernel (self):\n")
+        for t, c, k in dev[:45]:
+            f.write(f"  {t / 1e3:9.2f} ms {100 * t / busy:5.1f}%  x{c:<6d} {k[:120]}\n")
+        f.write("\nhost (CPU self time):\n")
+        f.write(ka.table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=70))
+    print(f"profile of {nsteps} steps -> {path}", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", choices=["ref_cuda", "b200"], required=True)
@@ -477,6 +511,8 @@ def main():
     ap.add_argument("--logprobs", type=int, default=None)
     ap.add_argument("--record", action="store_true", help="keep tokens / schedule in the JSON")
     ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--profile", default=None,
+                    help="START:COUNT:FILE - torch.profiler over COUNT engine steps from step START")
     ap.add_argument("--assets", default="/tmp/vltr_assets")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
@@ -491,7 +527,9 @@ def main():
                           swap_space=args.swap_space,
                           num_gpu_blocks_override=args.num_gpu_blocks)
     out = run_trace(llm, reqs, scores=args.scores, record_schedule=args.record,
-                    logprobs=args.logprobs, max_steps=args.max_steps)
+                    logprobs=args.logprobs, max_steps=args.max_steps,
+                    profile=((int(args.profile.split(":")[0]), int(args.profile.split(":")[1]),
+                              args.profile.split(":", 2)[2]) if args.profile else None))
     out["engine"] = info
     out["config"] = {k: v for k, v in vars(args).items()}
     if not args.record:

@@ -21,6 +21,15 @@ benchref) stage "bench.py --impl reference"
 trace7b) for arm in b200; do stage "7B trace $arm"
   timeout 900 python tools/engine_trace.py --arm $arm --model llama-2-7b --num-prompts 10000 --stop-after 1000 --json $O/e_7b_$arm.json > $O/e_7b_$arm.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
   grep TRACE $O/e_7b_$arm.log | tail -1 | head -c 1500; done;;
+predbench) stage "predictor bench"
+  timeout 600 python tools/predictor_bench.py > $O/predictor_bench.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  cat $O/predictor_bench.log | tail -30;;
+predtests) stage "predictor tests"
+  timeout 900 python -m pytest tests/test_gpu_predictor.py -x -q -m gpu -p no:cacheprovider > $O/pytest_pred.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  tail -5 $O/pytest_pred.log;;
+profile) for arm in b200 ref_cuda; do stage "profile $arm"
+  timeout 900 python tools/engine_trace.py --arm $arm --model llama-2-7b --num-prompts 10000 --stop-after 1000 --max-steps 260 --profile 200:40:$O/engine_profile_$arm.txt --json $O/e_prof_$arm.json > $O/e_prof_$arm.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  head -50 $O/engine_profile_$arm.txt; done;;
 esac
 done
 stage done

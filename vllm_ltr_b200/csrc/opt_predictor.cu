@@ -120,7 +120,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kBM = 128;      // UMMA M (one TMEM lane per output row)
 constexpr int kBK = 64;       // 64 halfs = 128 bytes = one swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 3;   // 3 x 32 KB (BN = 128): two CTAs per SM, one's epilogue under the other's MMAs
 constexpr int kGemmThreads = 128;
 
 template <int BN>
@@ -306,21 +306,53 @@ __global__ void __launch_bounds__(128)
     for (int i = lane; i < H; i += 32) y[i] = x[i];
     return;
   }
+  // H is a multiple of 64: every lane owns H/256 (+1) 16-byte chunks, kept in registers
+  constexpr int kMaxChunks = 8;                 // H <= 2048
+  const int nchunk = H / 8;
+  uint4 v[kMaxChunks];
   float s = 0.f;
-  for (int i = lane; i < H; i += 32) s += ST<T>::to_f(x[i]);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      v[c] = *reinterpret_cast<const uint4*>(x + ch * 8);
+      const T* e = reinterpret_cast<const T*>(&v[c]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += ST<T>::to_f(e[k]);
+    }
+  }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
   const float mean = s / H;
-  float v = 0.f;
-  for (int i = lane; i < H; i += 32) {
-    const float d = ST<T>::to_f(x[i]) - mean;
-    v += d * d;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    if (lane + 32 * c < nchunk) {
+      const T* e = reinterpret_cast<const T*>(&v[c]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = ST<T>::to_f(e[k]) - mean;
+        var += d * d;
+      }
+    }
   }
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  const float rstd = rsqrtf(v / H + eps);
-  for (int i = lane; i < H; i += 32)
-    y[i] = ST<T>::from_f((ST<T>::to_f(x[i]) - mean) * rstd * ST<T>::to_f(w[i]) + ST<T>::to_f(b[i]));
+  for (int m = 16; m >= 1; m >>= 1) var += __shfl_xor_sync(0xffffffffu, var, m);
+  const float rstd = rsqrtf(var / H + eps);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      const T* e = reinterpret_cast<const T*>(&v[c]);
+      alignas(16) T wv[8], bv[8], o[8];
+      *reinterpret_cast<uint4*>(wv) = __ldg(reinterpret_cast<const uint4*>(w + ch * 8));
+      *reinterpret_cast<uint4*>(bv) = __ldg(reinterpret_cast<const uint4*>(b + ch * 8));
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        o[k] = ST<T>::from_f((ST<T>::to_f(e[k]) - mean) * rstd * ST<T>::to_f(wv[k]) + ST<T>::to_f(bv[k]));
+      *reinterpret_cast<uint4*>(y + ch * 8) = *reinterpret_cast<uint4*>(o);
+    }
+  }
 }
 
 // causal varlen attention, head size 64.  qkv [M, 3H] (q | k | v), out [M, H].
@@ -751,6 +783,8 @@ extern "C" int vltr_opt_create(const vltr_opt_config* cfg, const vltr_opt_weight
              "opt_create: %d layers (max %d)", cfg->layers, VLTR_OPT_MAX_LAYERS);
   VLTR_CHECK(cfg->heads > 0 && cfg->hidden == cfg->heads * 64, VLTR_ERR_UNSUPPORTED,
              "opt_create: head size must be 64 (hidden %d, heads %d)", cfg->hidden, cfg->heads);
+  VLTR_CHECK(cfg->hidden <= 2048, VLTR_ERR_UNSUPPORTED,
+             "opt_create: hidden %d (LayerNorm keeps a row in registers: max 2048)", cfg->hidden);
   VLTR_CHECK(cfg->hidden % 64 == 0 && cfg->ffn % 64 == 0 && cfg->embed_dim % 64 == 0,
              VLTR_ERR_UNSUPPORTED, "opt_create: hidden / ffn / embed_dim must be multiples of 64");
   VLTR_CHECK(cfg->dtype == VLTR_F16 || cfg->dtype == VLTR_BF16, VLTR_ERR_UNSUPPORTED,

@@ -22,8 +22,11 @@ trace7b) for arm in b200; do stage "7B trace $arm"
   timeout 900 python tools/engine_trace.py --arm $arm --model llama-2-7b --num-prompts 10000 --stop-after 1000 --json $O/e_7b_$arm.json > $O/e_7b_$arm.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
   grep TRACE $O/e_7b_$arm.log | tail -1 | head -c 1500; done;;
 predbench) stage "predictor bench"
-  timeout 600 python tools/predictor_bench.py > $O/predictor_bench.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
-  cat $O/predictor_bench.log | tail -30;;
+  for v in "" "--no-pdl" "--gemm 1" "--gemm 1 --no-pdl"; do
+  echo "--- predictor_bench $v" >> $O/predictor_bench.log
+  timeout 600 python tools/predictor_bench.py $v >> $O/predictor_bench.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  done
+  grep -v Warn $O/predictor_bench.log | tail -80;;
 predtests) stage "predictor tests"
   timeout 900 python -m pytest tests/test_gpu_predictor.py -x -q -m gpu -p no:cacheprovider > $O/pytest_pred.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
   tail -5 $O/pytest_pred.log;;

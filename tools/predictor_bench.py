@@ -23,8 +23,15 @@ def main():
     ap.add_argument("--prompts", type=int, default=2000)
     ap.add_argument("--kind", default="125m")
     ap.add_argument("--batch-tokens", type=int, default=16384)
+    ap.add_argument("--gemm", type=int, default=0, help="1: one-tile-per-CTA GEMM (A/B)")
+    ap.add_argument("--no-pdl", action="store_true",
+                    help="serialise kernels (per-kernel times in the breakdown are then exact)")
     args = ap.parse_args()
+    from vllm_ltr_b200._lib import tune
     from vllm_ltr_b200.predictor import OPTPredictor, dummy_checkpoint
+    tune("opt_gemm", args.gemm)
+    if args.no_pdl:
+        tune("pdl", 0)
     rng = np.random.default_rng(0)
     lens = np.clip(np.round(np.exp(rng.normal(5.0, 1.0, args.prompts))), 4, 2048).astype(int)
     prompts = [rng.integers(3, 50000, int(n)).tolist() for n in lens]

@@ -78,6 +78,7 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
 struct Tune {
   long long attn_warps, attn_stages, attn_ctas, attn_slots, attn_cap_tokens, attn_min_tokens;
   long long attn_trace;      // device pointer: per-warp globaltimer stamps (tools/attn_tune.py)
+  long long opt_gemm;        // 1: one-tile-per-CTA predictor GEMM instead of the persistent one
 };
 extern Tune g_tune;
 

@@ -249,6 +249,181 @@ __global__ void __launch_bounds__(kGemmThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// dense layer, persistent form (the default): one CTA per SM walks a strided list of output tiles
+// with three specialised roles, so the epilogue of tile i runs under the MMAs of tile i+1:
+//   warp 0      TMA producer   - A / W k-blocks into a kStages2-deep shared-memory ring
+//   warp 1      MMA issuer     - tcgen05.mma into one of TWO TMEM accumulators (2 x BN columns)
+//   warps 2..5  epilogue       - tcgen05.ld their 32-lane quarter, bias / ReLU in registers, round
+//                                to T, transpose through a padded shared-memory slab so that the
+//                                residual read and the store are full 128-byte rows (4 rows per
+//                                warp instruction) instead of one 16-byte piece per row
+// Barriers: full/empty per ring stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator
+// (MMA <-> epilogue).  K for these layers is only 768..3072 (12..48 k-blocks), so without the
+// overlap the epilogue is as long as the main loop.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGemm2Threads = 192;
+constexpr int kSlabRow = 144;                       // 128 B of T + 16 B pad: conflict-free both ways
+template <int BN>
+__host__ __device__ constexpr int gemm2_stages() { return BN == 128 ? 5 : 6; }
+template <int BN>
+__host__ __device__ constexpr int gemm2_smem_bytes() {
+  return gemm2_stages<BN>() * (kBM * kBK * 2 + BN * kBK * 2) + 4 * 32 * kSlabRow + 1024 + 256;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <typename T, int BN, bool RELU>
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+    gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                              const __grid_constant__ CUtensorMap map_b, T* __restrict__ D,
+                              const T* __restrict__ bias, const T* __restrict__ resid, int M, int N,
+                              int K) {
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int S = gemm2_stages<BN>();
+  constexpr uint32_t A_BYTES = kBM * kBK * 2, B_BYTES = BN * kBK * 2, STAGE = A_BYTES + B_BYTES;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t slab0 = base + S * STAGE;
+  const uint32_t bars = slab0 + 4 * 32 * kSlabRow;
+  const uint32_t full0 = bars, empty0 = bars + 8 * S, tfull0 = bars + 16 * S,
+                 tempty0 = tfull0 + 16, slot = tempty0 + 16;
+  unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));     // generic view of `base`
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_n = N / BN, num_m = (M + kBM - 1) / kBM, total = num_m * num_n;
+  const int nk = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 4);      // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, STAGE);
+          tma_load_2d(base + s * STAGE, &map_a, kb * kBK, m0, full0 + 8 * s);
+          tma_load_2d(base + s * STAGE + A_BYTES, &map_b, kb * kBK, n0, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc<T, BN>();
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        mbar_wait(tempty0 + 8 * buf, ((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t ad = make_desc_sw128(base + s * STAGE);
+          const uint64_t bd = make_desc_sw128(base + s * STAGE + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_f16(acc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * buf);
+      }
+    }
+  } else {
+    // ---- epilogue warps: TMEM lanes [32q, 32q+32) are the only ones warp (id % 4 == q) may read --
+    const int q = warp & 3;
+    const uint32_t slab = slab0 + (uint32_t)((warp - 2) * 32 * kSlabRow);
+    const unsigned char* slab_gen = gen + (slab - base);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+      const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+      const int buf = t & 1;
+      mbar_wait(tfull0 + 8 * buf, (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        // my row's 64 columns -> bias / relu -> T -> slab row (128 B)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld32(trow + c * 64 + h * 32, r);
+          const int col = n0 + c * 64 + h * 32;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            alignas(16) T o[8];
+            alignas(16) T bs[8];
+            if (bias != nullptr) *reinterpret_cast<uint4*>(bs) = __ldg(reinterpret_cast<const uint4*>(bias + col + v * 8));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(r[v * 8 + e]);
+              if (bias != nullptr) x += ST<T>::to_f(bs[e]);
+              if (RELU) x = fmaxf(x, 0.f);
+              o[e] = ST<T>::from_f(x);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(slab + lane * kSlabRow + h * 64 + v * 16),
+                         "r"(reinterpret_cast<uint4*>(o)->x), "r"(reinterpret_cast<uint4*>(o)->y),
+                         "r"(reinterpret_cast<uint4*>(o)->z), "r"(reinterpret_cast<uint4*>(o)->w)
+                         : "memory");
+          }
+        }
+        __syncwarp();
+        // transposed pass: 8 lanes cover one 128-byte row, 4 rows per instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+          const int row = m0 + q * 32 + rr;
+          if (row < M) {
+            uint4 val = *reinterpret_cast<const uint4*>(slab_gen + rr * kSlabRow + ch * 16);
+            const int64_t off = (int64_t)row * N + n0 + c * 64 + ch * 8;
+            if (resid != nullptr) {
+              alignas(16) T rs[8];
+              alignas(16) T o[8];
+              *reinterpret_cast<uint4*>(rs) = *reinterpret_cast<const uint4*>(resid + off);
+              const T* lin = reinterpret_cast<const T*>(&val);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)    // linear output already rounded to T, then + residual
+                o[e] = ST<T>::from_f(ST<T>::to_f(lin[e]) + ST<T>::to_f(rs[e]));
+              val = *reinterpret_cast<uint4*>(o);
+            }
+            st_16(D + off, val);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------
 // out[t, :] = tok[ids[t], :E] (+ pos[positions[t] + 2, :] when ADD_POS; requires E == H then)
@@ -637,16 +812,31 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int b
 template <typename T, int BN, bool RELU>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const void* bias,
                        const void* resid, int M, int N, int K, cudaStream_t stream) {
-  auto kern = gemm_tn_kernel<T, BN, RELU>;
+  if (g_tune.opt_gemm == 1) {       // the one-tile-per-CTA form (A/B knob, tools/predictor_bench.py)
+    auto kern = gemm_tn_kernel<T, BN, RELU>;
+    static bool configured = false;
+    if (!configured) {
+      VLTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     gemm_smem_bytes<BN>()));
+      configured = true;
+    }
+    dim3 grid(N / BN, (M + kBM - 1) / kBM);
+    launch(kern, grid, dim3(kGemmThreads), (size_t)gemm_smem_bytes<BN>(), stream, ma, mb, (T*)D,
+           (const T*)bias, (const T*)resid, M, N, K);
+    VLTR_LAUNCH_CHECK("opt_gemm");
+    return VLTR_OK;
+  }
+  auto kern = gemm_tn_persistent_kernel<T, BN, RELU>;
   static bool configured = false;
   if (!configured) {
     VLTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   gemm_smem_bytes<BN>()));
+                                   gemm2_smem_bytes<BN>()));
     configured = true;
   }
-  dim3 grid(N / BN, (M + kBM - 1) / kBM);
-  launch(kern, grid, dim3(kGemmThreads), (size_t)gemm_smem_bytes<BN>(), stream, ma, mb, (T*)D,
-         (const T*)bias, (const T*)resid, M, N, K);
+  const int total = (N / BN) * ((M + kBM - 1) / kBM);
+  const int ctas = total < num_sms() ? total : num_sms();
+  launch(kern, dim3(ctas), dim3(kGemm2Threads), (size_t)gemm2_smem_bytes<BN>(), stream, ma, mb,
+         (T*)D, (const T*)bias, (const T*)resid, M, N, K);
   VLTR_LAUNCH_CHECK("opt_gemm");
   return VLTR_OK;
 }

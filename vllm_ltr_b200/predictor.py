@@ -196,6 +196,11 @@ class OPTPredictor:
         self._ws_cap = (0, 0)
         self._host = None
         self._host_evt = None
+        # single-prompt forwards (the steady-state tick scores one new prompt) replay a CUDA graph
+        # per 64-token bucket: ~90 launches and 2 tensor-map encodes per dense layer become one
+        # graph launch.  Keyed by padded token count; dropped when the workspace is reallocated.
+        self.use_graphs = os.environ.get("VLTR_OPT_GRAPHS", "1") != "0"
+        self._graphs = {}
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -224,6 +229,7 @@ class OPTPredictor:
             n = lib.vltr_opt_workspace_bytes(self._handle, cap[0], cap[1])
             self._ws = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
             self._ws_cap = cap
+            self._graphs.clear()          # captured launches point into the old workspace
         off = (-self._ws.data_ptr()) % 256
         return self._ws.data_ptr() + off, self._ws.numel() - off
 
@@ -246,12 +252,60 @@ class OPTPredictor:
             i = j
         return out
 
+    def _forward_graph(self, prompt: Sequence[int], out: torch.Tensor) -> None:
+        """One prompt through the captured forward of its 64-token bucket.  Rows past the prompt
+        are padding (token 0 at position 0): every op of the forward is row-wise except attention,
+        which reads cu_seqlens = [0, len] and never touches them."""
+        L = len(prompt)
+        mp = (L + 63) // 64 * 64
+        need = 2 * mp + 3                                  # ids | positions | cu_seqlens | last
+        ent = self._graphs.get(mp)
+        if ent is None:
+            ws, ws_bytes = self._workspace(max(mp, 2048), 16)
+            ent = {"dev": torch.zeros(need, dtype=torch.int32, device=self.device),
+                   "host": torch.zeros(need, dtype=torch.int32).pin_memory(),
+                   "out": torch.empty(1, self.num_labels, dtype=torch.float32, device=self.device),
+                   "evt": None, "graph": None}
+            base = ent["dev"].data_ptr()
+
+            def call():
+                check(lib.vltr_opt_forward(self._handle, base, base + 4 * mp, base + 8 * mp,
+                                           base + 8 * mp + 8, mp, 1, mp, ws,
+                                           ctypes.c_size_t(ws_bytes), ent["out"].data_ptr(),
+                                           torch._C._cuda_getCurrentRawStream(self.device.index)))
+            ent["dev"][2 * mp + 1] = 1                     # a valid 1-token prompt for the warm-up
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.device(self.device), torch.cuda.stream(side):
+                call()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.device(self.device), torch.cuda.graph(g):
+                call()
+            ent["graph"] = g
+            self._graphs[mp] = ent
+        if ent["evt"] is not None:
+            ent["evt"].synchronize()                       # previous copy out of the pinned buffer
+        h = ent["host"].numpy()
+        h[:L] = prompt
+        h[L:mp] = 0
+        h[mp:mp + L] = range(L)
+        h[mp + L:2 * mp] = 0
+        h[2 * mp], h[2 * mp + 1], h[2 * mp + 2] = 0, L, L - 1
+        ent["dev"].copy_(ent["host"], non_blocking=True)
+        ent["evt"] = torch.cuda.Event()
+        ent["evt"].record()
+        ent["graph"].replay()
+        out.copy_(ent["out"])
+
     def _forward(self, batch: Sequence[Sequence[int]], out: torch.Tensor) -> None:
         lens = [len(p) for p in batch]
         if min(lens) < 1:
             raise RuntimeError("empty prompt")
         if max(lens) > self.max_pos:
             raise RuntimeError(f"prompt of {max(lens)} tokens exceeds max_position_embeddings")
+        if len(batch) == 1 and self.use_graphs and (lens[0] + 63) // 64 * 64 <= self.max_pos:
+            return self._forward_graph(batch[0], out)
         n, m = len(batch), sum(lens)
         # one pinned staging buffer (persistent, grow-only), one H2D copy:
         # ids | positions | cu_seqlens | last_rows

@@ -84,15 +84,46 @@ def test_paged_attention_ragged(ops, version, num_heads, block_size, dtype, kv_c
 @pytest.mark.parametrize("num_heads,dtype,kv", [((32, 32), torch.half, "auto"),
                                                 ((32, 8), torch.bfloat16, "auto"),
                                                 ((32, 8), torch.bfloat16, "fp8"),
-                                                ((8, 1), torch.bfloat16, "auto")])
-def test_paged_attention_bench_shapes(ops, num_seqs, num_heads, dtype, kv):
-    """The micro-shapes of SURVEY.md section 8d: batch 1..256, the four (Hq, Hkv, dtype) configs,
-    ShareGPT-like contexts; batch 1 and 3 exercise the library-side context split of v1."""
+                                                ((8, 1), torch.bfloat16, "auto"),
+                                                ((4, 4), torch.half, "auto"),
+                                                ((4, 1), torch.bfloat16, "fp8")])
+@pytest.mark.parametrize("split", [0, 1, -1])
+def test_paged_attention_bench_shapes(ops, num_seqs, num_heads, dtype, kv, split):
+    """The micro-shapes of SURVEY.md section 8d: batch 1..256, the (Hq, Hkv, dtype) configs of the
+    benchmark models and of their TP8 shards, ShareGPT-like contexts; batch 1 and 3 exercise the
+    library-side context split of v1.  `split`: the library's own choice between the one-launch
+    form (partitions merged by the last finisher) and the two-launch form of the latency-bound
+    regime (kernel-sized partitions + parallel merge kernel), then each of them forced."""
+    from vllm_ltr_b200._lib import tune
     c = util.attention_case(num_seqs, num_heads, 128, 16, dtype, kv, False, 7,
                             6000 if num_seqs <= 3 else 1500, DEV, num_blocks=8192)
-    for version in ("v1", "v2"):
-        out, _ = util.run_attention(ops, c, version)
-        _check(out, util.oracle_attention(c), kv)
+    tune("attn_split", split)
+    try:
+        for version in ("v1", "v2"):
+            out, _ = util.run_attention(ops, c, version)
+            _check(out, util.oracle_attention(c), kv)
+    finally:
+        tune("attn_split", 0)
+
+
+@pytest.mark.parametrize("min_tokens", [16, 64, 256])
+@pytest.mark.parametrize("num_heads", [(8, 1), (4, 4), (40, 2)])
+def test_paged_attention_split_partition_sizes(ops, min_tokens, num_heads):
+    """Two-launch form with small / large minimum partitions: ragged contexts around partition
+    edges, an empty one, a long one (many partitions for the merge kernel)."""
+    from vllm_ltr_b200._lib import tune
+    lens = [1, 15, 16, 17, 63, 64, 65, 127, 129, 0, 255, 257, 1000, 4097, 33, 8000]
+    c = util.attention_case(len(lens), num_heads, 128, 16, torch.bfloat16, "auto", True, 13, 0,
+                            DEV, context_lens=lens, num_blocks=1024)
+    tune("attn_split", 1)
+    tune("attn_min_tokens", min_tokens)
+    try:
+        out, _ = util.run_attention(ops, c, "v1")
+    finally:
+        tune("attn_split", 0)
+        tune("attn_min_tokens", 0)
+    _check(out, util.oracle_attention(c), "auto")
+    assert (out[9] == 0).all()
 
 
 def test_paged_attention_strided_query(ops):

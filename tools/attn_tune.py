@@ -27,7 +27,10 @@ DEV = "cuda:0"
 CFGS = {"7b-mha-bf16": (32, 32, torch.bfloat16, "auto"),
         "8b-gqa-bf16": (32, 8, torch.bfloat16, "auto"),
         "8b-gqa-fp8": (32, 8, torch.bfloat16, "fp8"),
-        "70b-tp8-bf16": (8, 1, torch.bfloat16, "auto")}
+        "70b-tp8-bf16": (8, 1, torch.bfloat16, "auto"),
+        "7b-tp8-bf16": (4, 4, torch.bfloat16, "auto"),
+        "7b-tp2-bf16": (16, 16, torch.bfloat16, "auto"),
+        "8b-tp8-bf16": (4, 1, torch.bfloat16, "auto")}
 
 
 def make_case(name, B, mode, seed=0, min_total_bytes=400 << 20, max_pools=12):
@@ -116,9 +119,13 @@ def main():
                  {"attn_ctas": 4, "attn_slots": 16}, {"attn_ctas": 4, "attn_slots": 16, "attn_cap_tokens": 256}],
         "r3": [{}, {"attn_slots": 12}, {"attn_slots": 16}, {"attn_cap_tokens": 256},
                {"attn_min_tokens": 128}, {"attn_min_tokens": 256}],
+        # round 2: the two-launch (split) mode of the latency-bound regime
+        "split": [{}, {"attn_split": -1}, {"attn_split": 1}, {"attn_split": 1, "attn_min_tokens": 32},
+                  {"attn_split": 1, "attn_min_tokens": 128}, {"attn_split": 1, "attn_min_tokens": 256},
+                  {"attn_split": 1, "attn_ctas": 2}, {"attn_split": 1, "attn_ctas": 4}],
     }[args.grid]
     keys = ("pdl", "attn_ctas", "attn_warps", "attn_stages", "attn_slots", "attn_cap_tokens",
-            "attn_min_tokens")
+            "attn_min_tokens", "attn_split")
     rows = []
     for spec in args.cases.split(","):
         name, B, mode = spec.split(":")

@@ -33,6 +33,12 @@ predtests) stage "predictor tests"
 profile) for arm in b200 ref_cuda; do stage "profile $arm"
   timeout 900 python tools/engine_trace.py --arm $arm --model llama-2-7b --num-prompts 10000 --stop-after 1000 --max-steps 260 --profile 200:40:$O/engine_profile_$arm.txt --json $O/e_prof_$arm.json > $O/e_prof_$arm.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
   head -50 $O/engine_profile_$arm.txt; done;;
+attntests) stage "attention tests"
+  timeout 1500 python -m pytest tests/test_gpu_attention.py tests/test_gpu_hotpath.py tests/test_gpu_properties.py -x -q -m gpu -p no:cacheprovider > $O/pytest_attn.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  tail -8 $O/pytest_attn.log;;
+attntune) stage "attention split tuning"
+  timeout 900 python tools/attn_tune.py --grid split --cases ${ATTN_CASES:-70b-tp8-bf16:256:trace,7b-tp8-bf16:256:trace,8b-tp8-bf16:256:trace,8b-gqa-bf16:64:trace,7b-tp2-bf16:256:trace,7b-mha-bf16:256:trace} --json $O/attn_tune_split.json > $O/attn_tune_split.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  cat $O/attn_tune_split.log;;
 esac
 done
 stage done

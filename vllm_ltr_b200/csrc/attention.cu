@@ -41,6 +41,7 @@ struct DevState {
   size_t ticket_cap[kTicketSlots] = {};
   char* ws[kTicketSlots] = {};       // fp32 partials of v1 launches with partitions
   size_t ws_bytes[kTicketSlots] = {};
+  int* plan_out = nullptr;           // kTicketSlots x 4 ints: partition size chosen by a split launch
   unsigned next_ticket = 0;
 };
 static DevState g_dev[64];
@@ -67,6 +68,8 @@ static int get_state(DevState** out) {
       VLTR_CUDA(cudaMalloc(&st->ws[slot], kWsFloor));
       st->ws_bytes[slot] = kWsFloor;
     }
+    VLTR_CUDA(cudaMalloc(&st->plan_out, sizeof(int) * 4 * kTicketSlots));
+    VLTR_CUDA(cudaMemset(st->plan_out, 0, sizeof(int) * 4 * kTicketSlots));
     VLTR_CUDA(cudaDeviceSynchronize());
     st->counters = c;
   }
@@ -116,6 +119,26 @@ static int ensure_tickets(DevState* st, int slot, size_t n, cudaStream_t stream)
   st->tickets[slot] = fresh;       // the previous table stays allocated (replayed graphs use it)
   st->ticket_cap[slot] = want;
   return VLTR_OK;
+}
+
+template <typename T>
+static int launch_merge_t(const Params& p, int head_size, int block_size, cudaStream_t stream) {
+  const dim3 grid((p.num_seqs * p.num_heads + 3) / 4), block(128);
+  switch (head_size) {
+#define VLTR_MERGE(DD) \
+    case DD: launch(merge_partials_kernel<T, DD>, grid, block, 0, stream, p, block_size); break;
+    VLTR_MERGE(64) VLTR_MERGE(80) VLTR_MERGE(96) VLTR_MERGE(112) VLTR_MERGE(128) VLTR_MERGE(256)
+#undef VLTR_MERGE
+    default: return fail(VLTR_ERR_UNSUPPORTED, "Unsupported head size: %d", head_size);
+  }
+  VLTR_LAUNCH_CHECK("paged_attention_merge");
+  return VLTR_OK;
+}
+static int launch_merge(const Params& p, int head_size, int block_size, int dtype,
+                        cudaStream_t stream) {
+  if (dtype == VLTR_F16) return launch_merge_t<__half>(p, head_size, block_size, stream);
+  if (dtype == VLTR_BF16) return launch_merge_t<__nv_bfloat16>(p, head_size, block_size, stream);
+  return launch_merge_t<float>(p, head_size, block_size, stream);
 }
 
 static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp_out,
@@ -225,6 +248,26 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     p.part_blocks_cap = pb;
     p.always_partial = 0;
     p.tmp_is_f32 = 1;
+    // Latency-bound regime: fewer than half the resident warps would get a (sequence, kv head,
+    // pass) group - tensor-parallel shards (70B at TP8: one kv head per GPU), small batches.  The
+    // kernel then sizes the partitions itself from the ACTUAL contexts (~1.5 items per resident
+    // warp, at least 64 tokens each) and the merge becomes a second, fully parallel launch
+    // (merge_partials_kernel) instead of the last finisher's chore.  attn_split: 0 = this policy,
+    // 1 = always when possible, -1 = never.
+    const bool can_split = p.use_plan && max_blocks > 1;
+    const bool want_split = g_tune.attn_split > 0 || (g_tune.attn_split == 0 && groups * 2 <= slots);
+    if (can_split && want_split) {
+      int pb_min = (int)floor_tokens / block_size;          // 64 tokens unless tuned
+      if (pb_min < 1) pb_min = 1;
+      if (pb_min < (max_blocks + 127) / 128) pb_min = (max_blocks + 127) / 128;   // nparts <= 128
+      if (pb_min < pb) {
+        p.adaptive = 1;
+        p.part_blocks = pb_min;
+        p.part_blocks_cap = pb;
+        p.n_part = (max_blocks + pb_min - 1) / pb_min;
+        p.defer_merge = 1;
+      }
+    }
   }
   int slot = 0;
   {
@@ -244,18 +287,23 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     if (rc) return rc;
     p.tickets = st->tickets[slot];
     p.counters = st->counters + 2 * (st->next_slot++ % kCounterSlots);
+    p.plan_out = p.defer_merge ? st->plan_out + 4 * slot : nullptr;
   }
   VLTR_CHECK((long long)num_seqs * num_kv_heads * p.passes <= (long long)st->ticket_cap[slot],
              VLTR_ERR_INVALID, "paged_attention: too many head groups");
 
+  int rc;
   if (!kv_fp8) {
-    return dtype == VLTR_F16    ? launch_mode_f16(p, head_size, block_size, stream)
-           : dtype == VLTR_BF16 ? launch_mode_bf16(p, head_size, block_size, stream)
-                                : launch_mode_f32(p, head_size, block_size, stream);
-  }
-  return dtype == VLTR_F16    ? launch_mode_f16_fp8(p, head_size, block_size, stream)
+    rc = dtype == VLTR_F16    ? launch_mode_f16(p, head_size, block_size, stream)
+         : dtype == VLTR_BF16 ? launch_mode_bf16(p, head_size, block_size, stream)
+                              : launch_mode_f32(p, head_size, block_size, stream);
+  } else {
+    rc = dtype == VLTR_F16    ? launch_mode_f16_fp8(p, head_size, block_size, stream)
          : dtype == VLTR_BF16 ? launch_mode_bf16_fp8(p, head_size, block_size, stream)
                               : launch_mode_f32_fp8(p, head_size, block_size, stream);
+  }
+  if (rc != VLTR_OK || !p.defer_merge) return rc;
+  return launch_merge(p, head_size, block_size, dtype, stream);
 }
 
 }  // namespace attn

@@ -76,6 +76,8 @@ struct Params {
   int* counters;                // [0] next item, [1] finished warps   (self-resetting)
   int* tickets;                 // [num_seqs * passes * num_kv_heads] partition tickets, all zero
   long long* trace;             // development: 16 stamps per warp (tools/attn_tune.py) or null
+  int defer_merge;              // 1: partitions are merged by merge_partials_kernel (second launch)
+  int* plan_out;                // defer_merge: [0] = KV blocks per partition the kernel chose
 };
 // per-warp timeline for tools/attn_tune.py --trace: build with `make EXTRA=-DVLTR_ATTN_TRACE=1`
 // (kept out of the production build: the extra live state costs registers in the tile loop)
@@ -704,6 +706,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   pdl_wait();
   pdl_trigger();
   if (tr != nullptr && lane == 0) tr[1] = gtime();
+  if (p.plan_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.plan_out[0] = part_blocks;
   Item cur, nxt;
   nxt.valid = 0;
   int pend = fetch_id(p, lane);
@@ -1171,7 +1174,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
     // ---- merge: the warp that publishes a sequence's LAST partition combines them all ------------
     // (reference: paged_attention_v2_reduce_kernel, :511-602: weights exp_sum_j*exp(max_j-max) /
     // (sum + 1e-6) over per-partition normalised outputs)
-    if (cur.nparts > 1) {
+    if (cur.nparts > 1 && !p.defer_merge) {
       __threadfence();
       __syncwarp();
       const int gid = (seq * p.passes + cur.pass) * p.num_kv_heads + kvh;
@@ -1209,6 +1212,97 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       p.counters[0] = 0;
       p.counters[1] = 0;
       __threadfence();
+    }
+  }
+}
+
+// ---- second launch of the latency-bound regime ---------------------------------------------------
+// When a launch has far fewer (sequence, kv-head) groups than the machine has resident warps
+// (tensor-parallel shards: 70B at TP8 is 1 kv head per GPU; small batches), contexts are cut into
+// many short partitions so that every warp streams a few KV tiles - and then merging a sequence's
+// partitions inside the main kernel would put nheads x nparts dependent L2 round trips on ONE warp
+// at the very end of the launch (measured: up to 20 us of a 46 us launch, profiles/
+// r01_attn_tune_timeline.txt).  Here the merge is its own grid instead: one warp per
+// (sequence, query head), all of them in parallel, launched with programmatic dependent launch so
+// that it is resident when the main kernel drains.  Same arithmetic as merge_partials (reference:
+// paged_attention_v2_reduce_kernel, attention_kernels.cu:511-602).
+template <typename T, int D>
+__global__ void __launch_bounds__(128) merge_partials_kernel(const __grid_constant__ Params p, int BS) {
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  pdl_wait();          // the main kernel has completed: partials and plan_out are visible
+  pdl_trigger();
+  if (idx >= p.num_seqs * p.num_heads) return;
+  const int seq = idx / p.num_heads;
+  const int part_tokens = __ldcg(p.plan_out) * BS;
+  const int ctx = p.context_lens[seq];
+  const int np = (ctx + part_tokens - 1) / part_tokens;
+  if (np <= 1) return;                       // single partition: the main kernel stored the result
+  const int64_t base = (int64_t)idx * p.n_part;
+  constexpr int KW = 4;                      // partitions per lane: np <= 128 (host guarantees)
+  float mj[KW], sj[KW];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KW; ++k) {
+    const int j = lane + 32 * k;
+    mj[k] = j < np ? __ldcg(p.max_logits + base + j) : -INFINITY;
+    sj[k] = j < np ? __ldcg(p.exp_sums + base + j) : 0.f;
+    m = fmaxf(m, mj[k]);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KW; ++k) {
+    sj[k] = lane + 32 * k < np ? sj[k] * expf(mj[k] - m) : 0.f;
+    sum += sj[k];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = __fdividef(1.0f, sum + 1e-6f);
+  constexpr int NV = (D + 127) / 128;
+  float4 a[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int JB = 8;                      // partial rows in flight per lane
+  for (int j0 = 0; j0 < np; j0 += JB) {
+    float4 v[JB][NV];
+    float w[JB];
+#pragma unroll
+    for (int jj = 0; jj < JB; ++jj) {
+      const int j = min(j0 + jj, np - 1);
+      float wk = 0.f;
+#pragma unroll
+      for (int k = 0; k < KW; ++k)            // owner lane (j & 31) holds it in slot j >> 5
+        if ((j >> 5) == k) wk = __shfl_sync(0xffffffffu, sj[k], j & 31);
+      w[jj] = j0 + jj < np ? wk * inv : 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int d = 4 * lane + 128 * i;
+        v[jj][i] = (D % 128 == 0 || d < D)
+                       ? load_cg_4<T>(p.tmp_out, (base + j) * D + d, p.tmp_is_f32 != 0)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        a[i].x += v[jj][i].x * w[jj];
+        a[i].y += v[jj][i].y * w[jj];
+        a[i].z += v[jj][i].z * w[jj];
+        a[i].w += v[jj][i].w * w[jj];
+      }
+  }
+  T* o = reinterpret_cast<T*>(p.out) + (int64_t)idx * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int d = 4 * lane + 128 * i;
+    if (D % 128 == 0 || d < D) {
+      o[d] = ST<T>::from_f(a[i].x);
+      o[d + 1] = ST<T>::from_f(a[i].y);
+      o[d + 2] = ST<T>::from_f(a[i].z);
+      o[d + 3] = ST<T>::from_f(a[i].w);
     }
   }
 }

@@ -79,6 +79,7 @@ struct Tune {
   long long attn_warps, attn_stages, attn_ctas, attn_slots, attn_cap_tokens, attn_min_tokens;
   long long attn_trace;      // device pointer: per-warp globaltimer stamps (tools/attn_tune.py)
   long long opt_gemm;        // 1: one-tile-per-CTA predictor GEMM instead of the persistent one
+  long long attn_split;      // paged attention two-launch (split) mode: 0 policy, 1 always, -1 never
 };
 extern Tune g_tune;
 

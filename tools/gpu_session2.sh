@@ -39,6 +39,10 @@ attntests) stage "attention tests"
 attntune) stage "attention split tuning"
   timeout 900 python tools/attn_tune.py --grid split --cases ${ATTN_CASES:-70b-tp8-bf16:256:trace,7b-tp8-bf16:256:trace,8b-tp8-bf16:256:trace,8b-gqa-bf16:64:trace,7b-tp2-bf16:256:trace,7b-mha-bf16:256:trace} --json $O/attn_tune_split.json > $O/attn_tune_split.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
   cat $O/attn_tune_split.log;;
+attntrace) stage "attention timeline (trace build)"
+  VLTR_LIB=$PWD/vllm_ltr_b200/libvllm_ltr_b200_trace.so timeout 600 python tools/attn_tune.py --trace --cases ${ATTN_CASES:-70b-tp8-bf16:256:trace,7b-tp8-bf16:256:trace} > $O/attn_trace.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
+  VLTR_PDL=0 VLTR_LIB=$PWD/vllm_ltr_b200/libvllm_ltr_b200_trace.so timeout 600 python tools/attn_tune.py --trace --cases 70b-tp8-bf16:256:trace >> $O/attn_trace.log 2>&1
+  cat $O/attn_trace.log;;
 esac
 done
 stage done

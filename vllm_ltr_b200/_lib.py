@@ -8,7 +8,9 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvllm_ltr_b200.so")
+# VLTR_LIB: development builds of the same library (e.g. the -DVLTR_ATTN_TRACE=1 variant that
+# tools/attn_tune.py --trace needs); the default is the in-tree product build
+LIB_PATH = os.environ.get("VLTR_LIB") or os.path.join(_HERE, "libvllm_ltr_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

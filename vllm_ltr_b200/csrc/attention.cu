@@ -248,14 +248,14 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     p.part_blocks_cap = pb;
     p.always_partial = 0;
     p.tmp_is_f32 = 1;
-    // Latency-bound regime: fewer than half the resident warps would get a (sequence, kv head,
-    // pass) group - tensor-parallel shards (70B at TP8: one kv head per GPU), small batches.  The
+    // Latency-bound regime: not every resident warp would get a (sequence, kv head, pass) group
+    // of its own - tensor-parallel shards (70B at TP8: one kv head per GPU), small batches.  The
     // kernel then sizes the partitions itself from the ACTUAL contexts (~1.5 items per resident
     // warp, at least 64 tokens each) and the merge becomes a second, fully parallel launch
     // (merge_partials_kernel) instead of the last finisher's chore.  attn_split: 0 = this policy,
     // 1 = always when possible, -1 = never.
     const bool can_split = p.use_plan && max_blocks > 1;
-    const bool want_split = g_tune.attn_split > 0 || (g_tune.attn_split == 0 && groups * 2 <= slots);
+    const bool want_split = g_tune.attn_split > 0 || (g_tune.attn_split == 0 && groups <= slots);
     if (can_split && want_split) {
       int pb_min = (int)floor_tokens / block_size;          // 64 tokens unless tuned
       if (pb_min < 1) pb_min = 1;

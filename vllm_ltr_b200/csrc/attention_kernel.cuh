@@ -577,7 +577,19 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
       if (lane == 0 && mine != 0) atomicAdd(&hist[131], mine);
       __syncthreads();
       const long long tiles = (long long)hist[131] * p.num_kv_heads * p.passes;
-      const long long want_items = ((long long)gridDim.x * nwarps * 3) / 2;
+      // Many groups (more than half a warp-wave of (sequence, kv head, pass) groups): about 1.5
+      // items per resident warp, so the longest-first queue can balance.  Few groups (TP shards
+      // with one or two kv heads, small batches): everything in ONE wave - every warp streams
+      // its few tiles exactly once and nobody queues behind a long item.  Every group adds about
+      // half an item of rounding (its partial last partition).  Measured: profiles/
+      // r02_attn_split.txt.
+      const long long warps_all = (long long)gridDim.x * nwarps;
+      const long long groups = (long long)p.num_seqs * p.num_kv_heads * p.passes;
+      long long want_items = (warps_all * 3) / 2;
+      if (groups * 2 <= warps_all) {
+        want_items = warps_all - groups / 2;
+        if (want_items < warps_all / 4) want_items = warps_all / 4;
+      }
       long long pb = (tiles + want_items - 1) / want_items;
       if (pb < p.part_blocks) pb = p.part_blocks;
       if (pb > p.part_blocks_cap) pb = p.part_blocks_cap;

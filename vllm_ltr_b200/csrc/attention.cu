@@ -257,7 +257,9 @@ static int run(bool v2, void* out, float* exp_sums, float* max_logits, void* tmp
     const bool can_split = p.use_plan && max_blocks > 1;
     const bool want_split = g_tune.attn_split > 0 || (g_tune.attn_split == 0 && groups <= slots);
     if (can_split && want_split) {
-      int pb_min = (int)floor_tokens / block_size;          // 64 tokens unless tuned
+      // at least 128 tokens per partition unless tuned (64 measured ~15% slower on the TP8 shards:
+      // twice the partials for the merge launch, profiles/r02_attn_split.txt)
+      int pb_min = (int)(g_tune.attn_min_tokens > 0 ? g_tune.attn_min_tokens : 128) / block_size;
       if (pb_min < 1) pb_min = 1;
       if (pb_min < (max_blocks + 127) / 128) pb_min = (max_blocks + 127) / 128;   // nparts <= 128
       if (pb_min < pb) {

@@ -235,7 +235,7 @@ int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias, const
  * x / out / resid are SYMMETRIC buffers: one per rank, same shape [num_tokens, hidden], every
  * rank holds all ranks' device pointers (x_ptrs[p] etc. are HOST arrays of `world` peer-mapped
  * device pointers, e.g. from torch.distributed._symmetric_memory); signal_pads[p] is rank p's
- * zero-initialised flag area (>= 8 KiB).  Every rank calls with the same sizes and epoch; one
+ * zero-initialised flag area (>= 8 KiB; the kernels use u32 indices 1024..1040 of it).  Every rank calls with the same sizes and epoch; one
  * kernel per rank, ranks rendezvous through epoch flags in the signal pads.
  *   vltr_tp_allreduce:               out[p] = sum_q x[q]                      on every rank p
  *   vltr_tp_allreduce_add_rms_norm:  resid[p] = (T)(sum_q x[q]) + resid ; out[p] = rms_norm(resid[p]) * weight
@@ -251,6 +251,13 @@ typedef struct vltr_tp_comm {
   void* const* out_ptrs;
   void* const* resid_ptrs;        /* may be NULL for vltr_tp_allreduce */
   uint32_t* const* signal_pads;
+  /* NVLS (optional): multicast mappings of the SAME symmetric buffers (one virtual address that
+   * reaches every rank's copy through the NVSwitch, e.g. symmetric-memory handle.multicast_ptr).
+   * All three non-NULL: rows are summed by multimem.ld_reduce in the switch and published by
+   * multimem.st; any NULL: `world` peer loads / stores per 16 bytes. */
+  const void* x_mc;
+  void* out_mc;
+  void* resid_mc;
 } vltr_tp_comm;
 int vltr_tp_allreduce(const vltr_tp_comm* comm, int num_tokens, int hidden_size, int dtype,
                       void* stream);

@@ -16,6 +16,48 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+class RefCustomAllreduce:
+    """The reference's custom all-reduce, for the timing comparison only (TEST INFRASTRUCTURE): the
+    buffer / IPC-handle plumbing of vllm/distributed/device_communicators/custom_all_reduce.py:
+    168-260 around oracle/_ref/ref_cuda_C.custom_ar (csrc/custom_all_reduce.cu unmodified)."""
+
+    @classmethod
+    def create(cls, rank, world, dev):
+        import glob
+        import importlib.util
+        hits = glob.glob(os.path.join(ROOT, "oracle", "_ref", "ref_cuda_C.*.so"))
+        if not hits or world not in (2, 4, 6, 8):
+            return None
+        try:
+            spec = importlib.util.spec_from_file_location("ref_cuda_C", hits[0])
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return cls(mod.custom_ar, rank, world)
+        except Exception as e:
+            if rank == 0:
+                print(f"reference custom all-reduce unavailable: {type(e).__name__}: {e}", flush=True)
+            return None
+
+    def __init__(self, ar, rank, world, max_size=8192 * 1024):
+        self.ar, self.world, self.max_size = ar, world, max_size
+        self.meta = torch.zeros(ar.meta_size() + max_size, dtype=torch.uint8, device="cuda")
+        self.buffer = torch.empty(max_size, dtype=torch.uint8, device="cuda")
+        self.rank_data = torch.empty(8 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        handles, offsets = self._ipc(self.meta)
+        self._ptr = ar.init_custom_ar(self.meta, self.rank_data, handles, offsets, rank, True)
+        handles, offsets = self._ipc(self.buffer)
+        ar.register_buffer(self._ptr, self.buffer, handles, offsets)
+
+    def _ipc(self, t):
+        data = t.untyped_storage()._share_cuda_()
+        allv = [None] * self.world
+        dist.all_gather_object(allv, (data[1], data[3]))
+        return [a[0] for a in allv], [a[1] for a in allv]
+
+    def all_reduce_reg(self, inp, out):
+        self.ar.all_reduce_reg(self._ptr, inp, out)
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     lr = int(os.environ.get("LOCAL_RANK", rank))
@@ -26,10 +68,18 @@ def main():
     from vllm_ltr_b200 import _C
     from vllm_ltr_b200.parallel import FusedTPComm
     ok = True
-    for dtype in (torch.bfloat16, torch.float16):
+    probe = FusedTPComm(8, 4096, torch.bfloat16, dev)
+    have_mc = probe.multimem
+    del probe
+    if rank == 0:
+        print(f"NVLS multicast mappings available: {have_mc}", flush=True)
+    for dtype, mm in [(d, m) for d in (torch.bfloat16, torch.float16, torch.float32)
+                      for m in ((True, False) if have_mc else (False,))]:
         for T, H in ((1, 4096), (7, 4096), (256, 4096), (256, 8192), (768, 8192), (300, 5120)):
+            if dtype == torch.float32 and H > 4096:
+                continue
             # both epoch modes: counted by the kernels (default, graph-safe) / passed by the host
-            comm = FusedTPComm(768, H, dtype, dev, device_epoch=(T != 7))
+            comm = FusedTPComm(768, H, dtype, dev, device_epoch=(T != 7), multimem=mm)
             g = torch.Generator(device=dev).manual_seed(100 + rank)
             x = torch.randint(-4, 5, (T, H), generator=g, device=dev).to(dtype)
             g0 = torch.Generator(device=dev).manual_seed(7)
@@ -47,7 +97,8 @@ def main():
             torch.cuda.synchronize()
             e_res = torch.equal(comm.resid[:T], want_res)
             diff = (out.float() - want_out.float()).abs().max().item()
-            e_out = diff <= 2 * float(want_out.float().abs().max()) * (2 ** -7 if dtype == torch.bfloat16 else 2 ** -10)
+            e_out = diff <= 2 * float(want_out.float().abs().max()) * (
+                2 ** -7 if dtype == torch.bfloat16 else (2 ** -10 if dtype == torch.float16 else 2 ** -20))
             comm.x[1][:T].copy_(x)
             torch.cuda.synchronize()
             dist.barrier()
@@ -57,7 +108,8 @@ def main():
             if not (e_res and e_out and e_plain):
                 ok = False
             if rank == 0:
-                print(f"{dtype} T={T} H={H}: resid exact={e_res} out maxdiff={diff:.3g} ok={e_out} plain exact={e_plain}", flush=True)
+                print(f"{dtype} T={T} H={H} {'multimem' if mm else 'peer ld/st'}: resid exact={e_res} "
+                      f"out maxdiff={diff:.3g} ok={e_out} plain exact={e_plain}", flush=True)
             del comm
     # CUDA-graph replay of a chain of exchanges (device-side epochs): three replays must give
     # what three eager rounds give
@@ -100,39 +152,102 @@ def main():
     if rank == 0:
         print(f"graph replay of 2 exchanges x 2 (after 1 eager round): exact={e_graph}", flush=True)
     del comm
-    # timing at the decode shapes
-    for T, H in ((256, 4096), (256, 8192), (768, 8192)):
+    # timing at the decode shapes: a CUDA graph of 40 exchanges (what a decode step replays: no
+    # host launch cost in the number), max over ranks; next to NCCL all_reduce + our norm kernel
+    # and to the REFERENCE's own custom all-reduce (csrc/custom_all_reduce.cuh:181-250 recompiled
+    # for sm_100a in oracle/_ref/ref_cuda_C, driven like vllm/distributed/device_communicators/
+    # custom_all_reduce.py:168-260 drives it: registered IPC buffers) + our norm kernel
+    from vllm_ltr_b200._lib import tune
+    ref_ar = RefCustomAllreduce.create(rank, world, dev)
+    for T, H in ((256, 4096), (256, 8192), (768, 8192), (64, 8192)):
         dtype = torch.bfloat16
-        comm = FusedTPComm(768, H, dtype, dev)
         x = torch.randn(T, H, device=dev).to(dtype)
         resid = torch.randn(T, H, device=dev).to(dtype)
         w = torch.ones(H, device=dev, dtype=dtype)
-        comm.x[0][:T].copy_(x)
-        comm.resid[:T].copy_(resid)
-
-        def fused():
-            comm.allreduce_add_rms_norm(0, w, 1e-5, T)
+        variants = []
+        comms = {}
+        for mm in ((True, False) if have_mc else (False,)):
+            comm = FusedTPComm(768, H, dtype, dev, multimem=mm)
+            comm.x[0][:T].copy_(x)
+            comm.resid[:T].copy_(resid)
+            comms[mm] = comm
+            variants.append((f"fused ({'multimem' if mm else 'peer ld/st'})",
+                             (lambda c: (lambda: c.allreduce_add_rms_norm(0, w, 1e-5, T)))(comm)))
 
         def nccl():
             dist.all_reduce(x)
             _C.ops.fused_add_rms_norm(x, resid, w, 1e-5)
 
-        for name, fn in (("fused", fused), ("nccl+norm", nccl)):
+        variants.append(("nccl all_reduce + norm kernel", nccl))
+        if ref_ar is not None and x.numel() * 2 <= ref_ar.max_size:
+            rbuf = ref_ar.buffer[:x.numel() * 2].view(dtype).view(T, H)
+            rbuf.copy_(x)
+            rout = torch.empty_like(x)
+
+            def refar():
+                ref_ar.all_reduce_reg(rbuf, rout)
+                _C.ops.fused_add_rms_norm(rout, resid, w, 1e-5)
+
+            variants.append(("reference custom_all_reduce (sm_100a build) + norm kernel", refar))
+        for name, fn in variants:
             for _ in range(5):
                 fn()
             torch.cuda.synchronize()
             dist.barrier()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    for _ in range(40):
+                        fn()
+            except Exception as e:              # NCCL capture can be refused: time it eagerly
+                graph = None
+                if rank == 0:
+                    print(f"   ({name}: not graph-capturable here: {type(e).__name__})", flush=True)
+            run = graph.replay if graph is not None else (lambda: [fn() for _ in range(40)])
+            run()
+            torch.cuda.synchronize()
+            dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(50):
-                fn()
+            for _ in range(5):
+                run()
             e1.record()
             torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device=dev)
+            t = torch.tensor([e0.elapsed_time(e1) / 200 * 1e3], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print(f"T={T} H={H} world={world} {name}: {t.item():.1f} us per exchange", flush=True)
-            x.copy_(torch.randn(T, H, device=dev).to(dtype))
+                print(f"T={T} H={H} world={world} {name}: {t.item():.1f} us per exchange"
+                      f"{'' if graph is not None else ' (eager)'}", flush=True)
+            del graph
+        # where one exchange's time goes (CTA 0 of every rank stamps the phases)
+        for mm, comm in comms.items():
+            buf = torch.zeros(8, dtype=torch.int64, device=dev)
+            rows = []
+            for _ in range(20):
+                torch.cuda.synchronize()
+                dist.barrier()
+                tune("tp_trace", buf.data_ptr())
+                comm.allreduce_add_rms_norm(0, w, 1e-5, T)
+                torch.cuda.synchronize()
+                tune("tp_trace", 0)
+                rows.append(buf.cpu().numpy().copy())
+            import numpy as np
+            r = np.array(rows[5:], dtype=np.float64)
+            ph = np.stack([r[:, 2] - r[:, 1], r[:, 3] - r[:, 2], r[:, 4] - r[:, 3],
+                           r[:, 5] - r[:, 4], r[:, 5] - r[:, 1]], axis=1).mean(axis=0) / 1e3
+            t = torch.tensor(ph, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                a = t.tolist()
+                print(f"   phases of one isolated exchange, {'multimem' if mm else 'peer ld/st'} "
+                      f"(CTA 0, max over ranks, us): start rendezvous {a[0]:.1f} | reduce+norm+"
+                      f"publish {a[1]:.1f} | system fence {a[2]:.1f} | end rendezvous {a[3]:.1f} | "
+                      f"total in kernel {a[4]:.1f}", flush=True)
+        del comms, variants
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank == 0:
         print("TP CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.barrier()

@@ -80,6 +80,8 @@ struct Tune {
   long long attn_trace;      // device pointer: per-warp globaltimer stamps (tools/attn_tune.py)
   long long opt_gemm;        // 1: one-tile-per-CTA predictor GEMM instead of the persistent one
   long long attn_split;      // paged attention two-launch (split) mode: 0 policy, 1 always, -1 never
+  long long tp_multimem;     // -1: ignore multicast mappings (peer loads / stores even when NVLS is there)
+  long long tp_trace;        // device pointer: 8 globaltimer stamps of the last exchange (tools/tp_check.py)
 };
 extern Tune g_tune;
 

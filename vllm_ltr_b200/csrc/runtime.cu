@@ -52,6 +52,8 @@ int vltr_tune(const char* key, long long value) {
   else if (k == "attn_trace") g_tune.attn_trace = value;
   else if (k == "opt_gemm") g_tune.opt_gemm = value;
   else if (k == "attn_split") g_tune.attn_split = value;
+  else if (k == "tp_multimem") g_tune.tp_multimem = value;
+  else if (k == "tp_trace") g_tune.tp_trace = value;
   else return vltr::fail(VLTR_ERR_INVALID, "vltr_tune: unknown key '%s'", k.c_str());
   return VLTR_OK;
 }

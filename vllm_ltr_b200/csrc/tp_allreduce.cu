@@ -23,6 +23,18 @@
 //     local acquire polls (no round trips, nothing to reset); one CTA per rank talks to the
 //     peers, the rest follow a device-scope flag; spins are bounded and trap instead of hanging.
 // The plain all-reduce (no norm) uses the same machinery for callers that need it.
+//
+// NVLS form (comm->x_mc / out_mc / resid_mc non-null: multicast mappings of the same symmetric
+// buffers, NVSwitch gen 3+): the owner of a row issues ONE multimem.ld_reduce per 16 bytes - the
+// switch fetches the row from all ranks and adds it up (fp32 accumulation) - instead of `world`
+// peer loads, and publishes the normalised row and the new residual with ONE multimem.st each
+// instead of `world` peer stores.  Same rendezvous, same ownership, same rounding points; the
+// summation order inside the switch is fixed by the hardware, and since only the owner reduces a
+// row every rank still receives identical bits.
+//
+// Launch: programmatic dependent launch like the other hot-path kernels - the grid is resident
+// and has read its epoch while the producer of x drains; the first cross-rank announcement comes
+// after griddepcontrol.wait (it says "my x is complete").
 #include "common.cuh"
 
 namespace vltr {
@@ -39,6 +51,10 @@ struct Comm {
   void* out[kMaxWorld];
   void* resid[kMaxWorld];
   uint32_t* pad[kMaxWorld];            // every rank's signal pad
+  const void* x_mc;                    // multicast mappings (NVLS) or null
+  void* out_mc;
+  void* resid_mc;
+  long long* trace;                    // development: 8 globaltimer stamps per call (CTA 0) or null
   int rank, world;
   uint32_t epoch;                      // 2 * call_index + 1 (start barrier), + 1 (end barrier);
                                        // 0: read it from this rank's counter in the signal pad
@@ -96,6 +112,48 @@ __device__ __forceinline__ void st_peer(void* p, const uint4& v) {
                : "memory");
 }
 
+// NVLS: one load that the switch turns into a reduction over every rank's copy
+template <typename T>
+__device__ __forceinline__ uint4 ld_reduce_mc(const void* p);
+template <>
+__device__ __forceinline__ uint4 ld_reduce_mc<__nv_bfloat16>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 ld_reduce_mc<__half>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 ld_reduce_mc<float>(const void* p) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_mc(void* p, const uint4& v) {   // one store, every rank's copy
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+               "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
@@ -111,13 +169,15 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // NORM: out = rms_norm(resid += allreduce(x)) ; !NORM: out = allreduce(x)
 // VPT: 16-byte vectors per thread (hidden <= VPT * kThreads * 16/sizeof(T))
-template <typename T, int VPT, bool NORM>
+template <typename T, int VPT, bool NORM, bool MC>
 __global__ void __launch_bounds__(kThreads)
     tp_fused_kernel(const __grid_constant__ Comm c, const T* __restrict__ weight, float eps,
                     int num_tokens, int hidden) {
   constexpr int N = 16 / sizeof(T);
   __shared__ float red[32];
   const int cta = blockIdx.x;
+  long long* tr = (c.trace != nullptr && cta == 0 && threadIdx.x == 0) ? c.trace : nullptr;
+  if (tr) tr[0] = gtimer();
   const int nvec = hidden / N;
   uint32_t* fin = c.pad[c.rank] + kPadBase + 9;
   // Device-epoch mode (CUDA-graph safe: nothing in the launch arguments changes from call to
@@ -125,12 +185,19 @@ __global__ void __launch_bounds__(kThreads)
   // advances by 2.  Every rank issues the same exchanges in the same order, so the counters
   // agree.  All CTAs read it before any can finish (the advance waits for all of them).
   uint32_t* ctr = c.pad[c.rank] + kPadBase + 10;
+  // (the counter is advanced by the previous exchange of THIS rank's stream: wait for it - and
+  // for the producer of x - before reading; under programmatic dependent launch everything above
+  // overlapped their tails)
+  pdl_wait();
+  pdl_trigger();
   const uint32_t epoch = c.epoch != 0 ? c.epoch : *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
+  if (tr) tr[1] = gtimer();
 
   // start: every rank's x is complete (its producing kernels finished before this one started).
   // CTA 0 announces this rank; every CTA polls the local pad for all peers' announcements.
   if (cta == 0) announce(c, epoch);
   wait_peers(c, epoch);
+  if (tr) tr[2] = gtimer();
 
   // rows owned by this rank: r, r + world, ...; CTAs of this rank stride over them
   for (int row = c.rank + cta * c.world; row < num_tokens; row += gridDim.x * c.world) {
@@ -146,17 +213,26 @@ __global__ void __launch_bounds__(kThreads)
     for (int k = 0; k < VPT; ++k) {
       const int v = threadIdx.x + k * kThreads;
       if (v < nvec) {
-        Vec16<T> part[kMaxWorld];
+        if constexpr (MC) {
+          // the switch adds the row up (fp32 accumulate) and returns it rounded to T
+          Vec16<T> sum;
+          *reinterpret_cast<uint4*>(&sum) =
+              ld_reduce_mc<T>(reinterpret_cast<const T*>(c.x_mc) + off + (int64_t)v * N);
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world)
-            *reinterpret_cast<uint4*>(&part[p]) =
-                ld_peer(reinterpret_cast<const T*>(c.x[p]) + off + (int64_t)v * N);
+          for (int j = 0; j < N; ++j) acc[k][j] = ST<T>::to_f(sum.v[j]);
+        } else {
+          Vec16<T> part[kMaxWorld];
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world)
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world)
+              *reinterpret_cast<uint4*>(&part[p]) =
+                  ld_peer(reinterpret_cast<const T*>(c.x[p]) + off + (int64_t)v * N);
 #pragma unroll
-            for (int j = 0; j < N; ++j) acc[k][j] += ST<T>::to_f(part[p].v[j]);
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world)
+#pragma unroll
+              for (int j = 0; j < N; ++j) acc[k][j] += ST<T>::to_f(part[p].v[j]);
+        }
       }
     }
     float ss = 0.f;
@@ -202,14 +278,21 @@ __global__ void __launch_bounds__(kThreads)
           o = z[k];
         }
         // publish the row to every rank
+        if constexpr (MC) {
+          st_mc(reinterpret_cast<T*>(c.out_mc) + off + (int64_t)v * N, *reinterpret_cast<uint4*>(&o));
+          if constexpr (NORM)
+            st_mc(reinterpret_cast<T*>(c.resid_mc) + off + (int64_t)v * N,
+                  *reinterpret_cast<uint4*>(&z[k]));
+        } else {
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p) {
-          if (p < c.world) {
-            st_peer(reinterpret_cast<T*>(c.out[p]) + off + (int64_t)v * N,
-                    *reinterpret_cast<uint4*>(&o));
-            if constexpr (NORM)
-              st_peer(reinterpret_cast<T*>(c.resid[p]) + off + (int64_t)v * N,
-                      *reinterpret_cast<uint4*>(&z[k]));
+          for (int p = 0; p < kMaxWorld; ++p) {
+            if (p < c.world) {
+              st_peer(reinterpret_cast<T*>(c.out[p]) + off + (int64_t)v * N,
+                      *reinterpret_cast<uint4*>(&o));
+              if constexpr (NORM)
+                st_peer(reinterpret_cast<T*>(c.resid[p]) + off + (int64_t)v * N,
+                        *reinterpret_cast<uint4*>(&z[k]));
+            }
           }
         }
       }
@@ -218,10 +301,12 @@ __global__ void __launch_bounds__(kThreads)
   // end: all rows of all ranks have landed everywhere.  The last CTA of this rank to finish its
   // peer stores announces (one system-scope release by one thread covers the CTA's stores: the
   // CTA barrier orders them before it) and waits for the peers.
+  if (tr) tr[3] = gtimer();
   __syncthreads();
   __shared__ int s_last;
   if (threadIdx.x == 0) {
     __threadfence_system();
+    if (tr) tr[4] = gtimer();
     const uint32_t done = atomicAdd(fin, 1u);
     s_last = done == gridDim.x - 1;
     if (s_last) *fin = 0u;
@@ -231,6 +316,10 @@ __global__ void __launch_bounds__(kThreads)
     announce(c, epoch + 1);
     wait_peers(c, epoch + 1);
     if (c.epoch == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(ctr) = epoch + 1u;
+  }
+  if (tr) {
+    tr[5] = gtimer();
+    tr[6] = s_last;
   }
 }
 
@@ -246,16 +335,23 @@ static int launch(const Comm& c, const void* weight, float eps, int num_tokens, 
   if (grid < 1) grid = 1;
   (void)rows_mine;
   const int vpt = (nvec + kThreads - 1) / kThreads;
-  if (vpt <= 1)
-    tp_fused_kernel<T, 1, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
-  else if (vpt <= 2)
-    tp_fused_kernel<T, 2, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
-  else if (vpt <= 4)
-    tp_fused_kernel<T, 4, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
-  else if (vpt <= 8)
-    tp_fused_kernel<T, 8, NORM><<<grid, kThreads, 0, stream>>>(c, (const T*)weight, eps, num_tokens, hidden);
+  const bool mc = c.x_mc != nullptr && g_tune.tp_multimem >= 0;
+#define VLTR_TP_LAUNCH(V)                                                                         \
+  do {                                                                                            \
+    if (mc)                                                                                       \
+      vltr::launch(tp_fused_kernel<T, V, NORM, true>, dim3(grid), dim3(kThreads), 0, stream, c,   \
+                   (const T*)weight, eps, num_tokens, hidden);                                    \
+    else                                                                                          \
+      vltr::launch(tp_fused_kernel<T, V, NORM, false>, dim3(grid), dim3(kThreads), 0, stream, c,  \
+                   (const T*)weight, eps, num_tokens, hidden);                                    \
+  } while (0)
+  if (vpt <= 1) VLTR_TP_LAUNCH(1);
+  else if (vpt <= 2) VLTR_TP_LAUNCH(2);
+  else if (vpt <= 4) VLTR_TP_LAUNCH(4);
+  else if (vpt <= 8) VLTR_TP_LAUNCH(8);
   else
     return fail(VLTR_ERR_UNSUPPORTED, "tp_allreduce: hidden size %d too large", hidden);
+#undef VLTR_TP_LAUNCH
   VLTR_LAUNCH_CHECK(NORM ? "tp_allreduce_add_rms_norm" : "tp_allreduce");
   return VLTR_OK;
 }
@@ -281,6 +377,14 @@ static int run(const vltr_tp_comm* comm, const void* weight, float eps, int num_
   c.rank = comm->rank;
   c.world = comm->world;
   c.epoch = comm->epoch;
+  c.x_mc = comm->x_mc;
+  c.out_mc = comm->out_mc;
+  c.resid_mc = norm ? comm->resid_mc : nullptr;
+  if (c.x_mc == nullptr || c.out_mc == nullptr || (norm && c.resid_mc == nullptr))
+    c.x_mc = nullptr;                 // all three multicast mappings or none
+  VLTR_CHECK(((uintptr_t)c.x_mc | (uintptr_t)c.out_mc | (uintptr_t)c.resid_mc) % 16 == 0,
+             VLTR_ERR_INVALID, "tp_allreduce: multicast mappings must be 16-byte aligned");
+  c.trace = reinterpret_cast<long long*>(g_tune.tp_trace);
   for (int p = 0; p < comm->world; ++p) {
     c.x[p] = comm->x_ptrs[p];
     c.out[p] = comm->out_ptrs[p];

@@ -66,12 +66,16 @@ class FusedTPComm:
     ``x[i]`` are the buffers the row-parallel GEMMs (o_proj, down_proj) write their partial sums
     into, ``out`` receives the normalised rows and ``resid`` is the running residual - all
     allocated from ``torch.distributed._symmetric_memory`` so every rank holds every rank's
-    pointers (plumbing only; the data path is the kernel in libvllm_ltr_b200)."""
+    pointers (plumbing only; the data path is the kernel in libvllm_ltr_b200).  When the
+    symmetric-memory handles carry multicast mappings (NVLS), the kernel sums rows inside the
+    NVSwitch (``multimem.ld_reduce``) and publishes them with ``multimem.st``
+    (``multimem=False`` / ``VLTR_TP_MULTIMEM=0`` keeps peer loads and stores)."""
 
     def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device,
                  group: Optional[dist.ProcessGroup] = None, num_inputs: int = 2,
-                 device_epoch: bool = True):
+                 device_epoch: bool = True, multimem: Optional[bool] = None):
         import ctypes
+        import os
 
         import torch.distributed._symmetric_memory as symm
         from ._lib import declare
@@ -85,18 +89,32 @@ class FusedTPComm:
         mk = lambda: symm.empty(max_tokens, hidden, dtype=dtype, device=device)
         self.x = [mk() for _ in range(num_inputs)]
         self.out, self.resid = mk(), mk()
+        # the rendezvous flags live in a buffer of our own (zeroed, 16 KiB; the kernels use u32
+        # indices 1024..1040), not in torch's signal pads: no assumption about their size or
+        # about which part of them torch's own barriers use
+        self.flags = symm.empty(4096, dtype=torch.int32, device=device)
+        self.flags.zero_()
         hx = [symm.rendezvous(t, name) for t in self.x]
         ho, hr = symm.rendezvous(self.out, name), symm.rendezvous(self.resid, name)
-        self._handles = hx + [ho, hr]
+        hf = symm.rendezvous(self.flags, name)
+        self._handles = hx + [ho, hr, hf]
         arr = lambda ptrs: (ctypes.c_void_p * self.world)(*[int(p) for p in ptrs])
         self._x_ptrs = [arr(h.buffer_ptrs) for h in hx]
         self._out_ptrs, self._resid_ptrs = arr(ho.buffer_ptrs), arr(hr.buffer_ptrs)
-        self._pads = arr(hx[0].signal_pad_ptrs)
+        self._pads = arr(hf.buffer_ptrs)
+        # NVLS: multicast mappings of the same buffers when the fabric offers them (0 otherwise)
+        mcp = lambda h: int(getattr(h, "multicast_ptr", 0) or 0)
+        self._x_mc = [mcp(h) for h in hx]
+        self._out_mc, self._resid_mc = mcp(ho), mcp(hr)
+        want_mc = multimem if multimem is not None else os.environ.get("VLTR_TP_MULTIMEM", "1") != "0"
+        self.multimem = bool(want_mc and all(self._x_mc) and self._out_mc and self._resid_mc)
 
         class _Comm(ctypes.Structure):
             _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int),
                         ("epoch", ctypes.c_uint32), ("x_ptrs", ctypes.c_void_p), ("out_ptrs", ctypes.c_void_p),
-                        ("resid_ptrs", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p)]
+                        ("resid_ptrs", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p),
+                        ("x_mc", ctypes.c_void_p), ("out_mc", ctypes.c_void_p),
+                        ("resid_mc", ctypes.c_void_p)]
 
         addr = lambda a: ctypes.cast(a, ctypes.c_void_p)
         # device_epoch: the kernels count the exchanges themselves (in the signal pad), so the
@@ -104,8 +122,12 @@ class FusedTPComm:
         # the host passes 2 * call_index + 1
         self.device_epoch = device_epoch
         self._calls = 0       # exchanges issued on these buffers (same on every rank)
+        mc = self.multimem
         self._comms = [_Comm(self.rank, self.world, 1, addr(xp), addr(self._out_ptrs),
-                             addr(self._resid_ptrs), addr(self._pads)) for xp in self._x_ptrs]
+                             addr(self._resid_ptrs), addr(self._pads),
+                             self._x_mc[i] if mc else None, self._out_mc if mc else None,
+                             self._resid_mc if mc else None)
+                       for i, xp in enumerate(self._x_ptrs)]
         _P = ctypes.c_void_p
         self._norm = declare("vltr_tp_allreduce_add_rms_norm", ctypes.c_int,
                              [_P, _P, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P])

@@ -50,8 +50,11 @@ class RefCustomAllreduce:
 
     def _ipc(self, t):
         data = t.untyped_storage()._share_cuda_()
+        handle = bytes(data[1])
+        if len(handle) == 65:        # torch >= 2.5 prefixes the cudaIpcMemHandle_t with a type byte
+            handle = handle[1:]
         allv = [None] * self.world
-        dist.all_gather_object(allv, (data[1], data[3]))
+        dist.all_gather_object(allv, (handle, data[3]))
         return [a[0] for a in allv], [a[1] for a in allv]
 
     def all_reduce_reg(self, inp, out):

@@ -569,7 +569,11 @@ def tp_parity_check(comm, dev, rank, world, T, H, dtype):
     dist.barrier()
     out = comm.allreduce_add_rms_norm(0, w, 1e-5, T).clone()
     torch.cuda.synchronize()
-    ok = torch.tensor([int(torch.equal(plain, s)), int(torch.equal(comm.resid[:T], want_res)),
+    # the residual is replicated or owner-local (row % world == rank), as the communicator says
+    mine = (torch.ones(T, dtype=torch.bool, device=dev) if getattr(comm, "replicate_residual", True)
+            else torch.arange(T, device=dev) % world == rank)
+    ok = torch.tensor([int(torch.equal(plain, s)),
+                       int(torch.equal(comm.resid[:T][mine], want_res[mine])),
                        int(torch.equal(out, want_out))], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     for t, k in zip((comm.x[0], comm.x[1], comm.resid), keep):

@@ -258,6 +258,11 @@ typedef struct vltr_tp_comm {
   const void* x_mc;
   void* out_mc;
   void* resid_mc;
+  /* 0: resid[p] is updated on every rank (the reference's replicated fused_add_rms_norm).
+   * 1: the new residual row is stored only on the rank that owns the row (row % world == rank) -
+   *    the only rank that reads it again (the next exchange adds to it); rows a rank does not own
+   *    are left untouched in its resid.  Halves the bytes an exchange publishes. */
+  int resid_local;
 } vltr_tp_comm;
 int vltr_tp_allreduce(const vltr_tp_comm* comm, int num_tokens, int hidden_size, int dtype,
                       void* stream);

@@ -81,11 +81,13 @@ def main():
     shapes = ((7, 4096), (256, 4096), (768, 8192)) if quick else (
         (1, 4096), (7, 4096), (256, 4096), (256, 8192), (768, 8192), (300, 5120))
     for dtype, mm in [(d, m) for d in dtypes for m in ((True, False) if have_mc else (False,))]:
-        for T, H in shapes:
+        for ti, (T, H) in enumerate(shapes):
+            rep = ti % 2 == 0         # alternate: replicated residual / owner-local residual
             if dtype == torch.float32 and H > 4096:
                 continue
             # both epoch modes: counted by the kernels (default, graph-safe) / passed by the host
-            comm = FusedTPComm(768, H, dtype, dev, device_epoch=(T != 7), multimem=mm)
+            comm = FusedTPComm(768, H, dtype, dev, device_epoch=(T != 7), multimem=mm,
+                               replicate_residual=rep)
             g = torch.Generator(device=dev).manual_seed(100 + rank)
             x = torch.randint(-4, 5, (T, H), generator=g, device=dev).to(dtype)
             g0 = torch.Generator(device=dev).manual_seed(7)
@@ -101,7 +103,12 @@ def main():
             dist.barrier()
             out = comm.allreduce_add_rms_norm(0, w, 1e-5, T)
             torch.cuda.synchronize()
-            e_res = torch.equal(comm.resid[:T], want_res)
+            if rep:
+                e_res = torch.equal(comm.resid[:T], want_res)
+            else:     # owner-local: my rows hold the new residual, the others are untouched
+                mine = torch.arange(T, device=dev) % world == rank
+                e_res = (torch.equal(comm.resid[:T][mine], want_res[mine])
+                         and torch.equal(comm.resid[:T][~mine], resid[~mine]))
             diff = (out.float() - want_out.float()).abs().max().item()
             e_out = diff <= 2 * float(want_out.float().abs().max()) * (
                 2 ** -7 if dtype == torch.bfloat16 else (2 ** -10 if dtype == torch.float16 else 2 ** -20))
@@ -114,13 +121,14 @@ def main():
             if not (e_res and e_out and e_plain):
                 ok = False
             if rank == 0:
-                print(f"{dtype} T={T} H={H} {'multimem' if mm else 'peer ld/st'}: resid exact={e_res} "
+                print(f"{dtype} T={T} H={H} {'multimem' if mm else 'peer ld/st'} "
+                      f"{'replicated' if rep else 'owner-local'} residual: resid exact={e_res} "
                       f"out maxdiff={diff:.3g} ok={e_out} plain exact={e_plain}", flush=True)
             del comm
     # CUDA-graph replay of a chain of exchanges (device-side epochs): three replays must give
     # what three eager rounds give
     T, H, dtype = 256, 4096, torch.bfloat16
-    comm = FusedTPComm(256, H, dtype, dev)
+    comm = FusedTPComm(256, H, dtype, dev, replicate_residual=True)
     g = torch.Generator(device=dev).manual_seed(200 + rank)
     xs = [torch.randint(-3, 4, (T, H), generator=g, device=dev).to(dtype) for _ in range(2)]
     w = torch.ones(H, device=dev, dtype=dtype)

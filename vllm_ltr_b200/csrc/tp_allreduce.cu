@@ -55,6 +55,7 @@ struct Comm {
   void* out_mc;
   void* resid_mc;
   long long* trace;                    // development: 8 globaltimer stamps per call (CTA 0) or null
+  int resid_local;                     // 1: the new residual row is stored on its owner only
   int rank, world;
   uint32_t epoch;                      // 2 * call_index + 1 (start barrier), + 1 (end barrier);
                                        // 0: read it from this rank's counter in the signal pad
@@ -277,12 +278,21 @@ __global__ void __launch_bounds__(kThreads)
         } else {
           o = z[k];
         }
+        // The residual of a row is only ever read again by the row's owner (the next exchange
+        // adds to it): with resid_local it stays here, and half of the published bytes - and of
+        // what the system fence below has to wait for - are gone.
+        if constexpr (NORM) {
+          if (c.resid_local)
+            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(c.resid[c.rank]) + off + (int64_t)v * N) =
+                *reinterpret_cast<uint4*>(&z[k]);
+        }
         // publish the row to every rank
         if constexpr (MC) {
           st_mc(reinterpret_cast<T*>(c.out_mc) + off + (int64_t)v * N, *reinterpret_cast<uint4*>(&o));
           if constexpr (NORM)
-            st_mc(reinterpret_cast<T*>(c.resid_mc) + off + (int64_t)v * N,
-                  *reinterpret_cast<uint4*>(&z[k]));
+            if (!c.resid_local)
+              st_mc(reinterpret_cast<T*>(c.resid_mc) + off + (int64_t)v * N,
+                    *reinterpret_cast<uint4*>(&z[k]));
         } else {
 #pragma unroll
           for (int p = 0; p < kMaxWorld; ++p) {
@@ -290,8 +300,9 @@ __global__ void __launch_bounds__(kThreads)
               st_peer(reinterpret_cast<T*>(c.out[p]) + off + (int64_t)v * N,
                       *reinterpret_cast<uint4*>(&o));
               if constexpr (NORM)
-                st_peer(reinterpret_cast<T*>(c.resid[p]) + off + (int64_t)v * N,
-                        *reinterpret_cast<uint4*>(&z[k]));
+                if (!c.resid_local)
+                  st_peer(reinterpret_cast<T*>(c.resid[p]) + off + (int64_t)v * N,
+                          *reinterpret_cast<uint4*>(&z[k]));
             }
           }
         }
@@ -385,6 +396,7 @@ static int run(const vltr_tp_comm* comm, const void* weight, float eps, int num_
   VLTR_CHECK(((uintptr_t)c.x_mc | (uintptr_t)c.out_mc | (uintptr_t)c.resid_mc) % 16 == 0,
              VLTR_ERR_INVALID, "tp_allreduce: multicast mappings must be 16-byte aligned");
   c.trace = reinterpret_cast<long long*>(g_tune.tp_trace);
+  c.resid_local = comm->resid_local != 0;
   for (int p = 0; p < comm->world; ++p) {
     c.x[p] = comm->x_ptrs[p];
     c.out[p] = comm->out_ptrs[p];

@@ -69,11 +69,17 @@ class FusedTPComm:
     pointers (plumbing only; the data path is the kernel in libvllm_ltr_b200).  When the
     symmetric-memory handles carry multicast mappings (NVLS), the kernel sums rows inside the
     NVSwitch (``multimem.ld_reduce``) and publishes them with ``multimem.st``
-    (``multimem=False`` / ``VLTR_TP_MULTIMEM=0`` keeps peer loads and stores)."""
+    (``multimem=False`` / ``VLTR_TP_MULTIMEM=0`` keeps peer loads and stores).
+
+    ``replicate_residual=False`` (default): the running residual of a row lives on the rank that
+    owns the row (``row % world == rank``) - the only rank that ever reads it again - so
+    ``resid`` is valid on a rank only for the rows it owns and an exchange publishes half the
+    bytes; ``True`` keeps the reference's replicated residual on every rank."""
 
     def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device,
                  group: Optional[dist.ProcessGroup] = None, num_inputs: int = 2,
-                 device_epoch: bool = True, multimem: Optional[bool] = None):
+                 device_epoch: bool = True, multimem: Optional[bool] = None,
+                 replicate_residual: bool = False):
         import ctypes
         import os
 
@@ -114,19 +120,20 @@ class FusedTPComm:
                         ("epoch", ctypes.c_uint32), ("x_ptrs", ctypes.c_void_p), ("out_ptrs", ctypes.c_void_p),
                         ("resid_ptrs", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p),
                         ("x_mc", ctypes.c_void_p), ("out_mc", ctypes.c_void_p),
-                        ("resid_mc", ctypes.c_void_p)]
+                        ("resid_mc", ctypes.c_void_p), ("resid_local", ctypes.c_int)]
 
         addr = lambda a: ctypes.cast(a, ctypes.c_void_p)
         # device_epoch: the kernels count the exchanges themselves (in the signal pad), so the
         # launch arguments never change and a step can be replayed from a CUDA graph; otherwise
         # the host passes 2 * call_index + 1
         self.device_epoch = device_epoch
+        self.replicate_residual = replicate_residual
         self._calls = 0       # exchanges issued on these buffers (same on every rank)
         mc = self.multimem
         self._comms = [_Comm(self.rank, self.world, 1, addr(xp), addr(self._out_ptrs),
                              addr(self._resid_ptrs), addr(self._pads),
                              self._x_mc[i] if mc else None, self._out_mc if mc else None,
-                             self._resid_mc if mc else None)
+                             self._resid_mc if mc else None, 0 if replicate_residual else 1)
                        for i, xp in enumerate(self._x_ptrs)]
         _P = ctypes.c_void_p
         self._norm = declare("vltr_tp_allreduce_add_rms_norm", ctypes.c_int,

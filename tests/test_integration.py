@@ -28,7 +28,7 @@ def test_install_engine_on_reference_shaped_objects(monkeypatch):
         scheduler=sched, model_config=types.SimpleNamespace(prefill_predictor_model_config=None),
         model_executor=types.SimpleNamespace(
             driver_worker=types.SimpleNamespace(model_runner=runner, cache_engine=ce)))
-    done = integration.install_engine(engine, prefill=False)
+    done = integration.install_engine(engine, prefill=False, attention_backend=False)
     assert done["scheduler"].startswith("LTR tick")
     assert sched._schedule.__func__ is ltr_scheduler.general_schedule
     assert done["predictor"].startswith("skipped")
@@ -39,5 +39,46 @@ def test_install_engine_on_reference_shaped_objects(monkeypatch):
     fcfs = types.SimpleNamespace(scheduler=types.SimpleNamespace(schedule_type="fcfs"),
                                  model_config=None, model_executor=None)
     done = integration.install_engine(fcfs, prefill=False)
+    assert done["attention_backend"].startswith("skipped")
     assert done["scheduler"].startswith("skipped") and done["swap"].startswith("skipped")
     assert done["sampler"].startswith("skipped") and done["decode_inputs"].startswith("skipped")
+
+
+def test_attention_backend_seam(monkeypatch):
+    """b2: every Attention layer of a built model gets a B200AttentionImpl carrying the arguments
+    its own impl was built with; the backend object keeps the reference's metadata / cache shape."""
+    import torch
+    R.import_reference()
+    monkeypatch.setattr(torch.cuda, "get_device_capability", lambda *a: (10, 0))
+    from vllm.attention.backends.abstract import AttentionBackend, AttentionImpl
+    from vllm.attention.layer import Attention
+
+    from vllm_ltr_b200 import attention_backend as ab
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = Attention(32, 128, 0.088, num_kv_heads=8)
+            self.b = Attention(8, 64, 0.125, alibi_slopes=[0.5] * 8)
+
+    torch.set_default_dtype(torch.float16)       # fp32 models get the xformers backend (absent here)
+    try:
+        m = Tiny()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    old_a = m.a.impl
+    assert ab.install(m) == 2 and ab.install(m) == 0          # idempotent
+    backend, impl_cls = ab.backend_classes()
+    assert issubclass(backend, AttentionBackend) and issubclass(impl_cls, AttentionImpl)
+    assert isinstance(m.a.impl, impl_cls) and m.a.impl.reference_impl is old_a
+    assert (m.a.impl.num_heads, m.a.impl.num_kv_heads, m.a.impl.head_size) == (32, 8, 128)
+    assert abs(m.a.impl.scale - 0.088) < 1e-9 and m.b.impl.alibi_slopes.shape == (8,)
+    assert backend.get_kv_cache_shape(10, 16, 8, 128) == (2, 10, 16 * 8 * 128)
+    assert backend.get_impl_cls() is impl_cls
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.a.impl.forward(torch.zeros(1, 32 * 128), torch.zeros(1, 8 * 128), torch.zeros(1, 8 * 128),
+                         torch.zeros(2, 4, 16 * 8 * 128),
+                         __import__("types").SimpleNamespace(
+                             kv_cache_dtype="auto", slot_mapping=torch.zeros(1, dtype=torch.long),
+                             num_prefill_tokens=0, num_decode_tokens=1, prefill_metadata=None,
+                             decode_metadata=None), 1.0)

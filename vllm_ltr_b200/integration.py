@@ -5,7 +5,8 @@
     from vllm import LLM
     llm = LLM(...)                          # the unmodified reference engine
     from vllm_ltr_b200.integration import install_engine
-    print(install_engine(llm.llm_engine))   # scheduler tick, predictor, swap path, decode inputs, sampler
+    print(install_engine(llm.llm_engine))   # scheduler tick, predictor, swap path, decode inputs,
+                                            # sampler, attention backend, prefill kernel
 
 Each piece is optional and reported; pieces whose preconditions do not hold (schedule_type is not
 "opt*", no predictor configured, Ray workers instead of an in-process driver worker) are skipped
@@ -32,6 +33,7 @@ def _release_aux_engine(aux) -> None:
 
 def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap: bool = True,
                    decode_inputs: bool = True, sampler: bool = True, prefill: bool = True,
+                   attention_backend: bool = True,
                    sampler_seed: Optional[int] = None,
                    release_reference_predictor: bool = True) -> Dict[str, str]:
     done: Dict[str, str] = {}
@@ -96,6 +98,19 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
                                    "other request goes to the engine's own Sampler)")
             else:
                 done["sampler"] = "skipped: model has no .sampler attribute"
+
+    if attention_backend:
+        model = getattr(runner, "model", None)
+        if model is not None:
+            try:
+                from . import attention_backend as ab
+                n = ab.install(model)
+                done["attention_backend"] = (f"B200AttentionImpl on {n} Attention layers: cache "
+                                             "append, prefill and decode attention issued directly")
+            except ImportError as e:
+                done["attention_backend"] = f"skipped: {e}"
+        else:
+            done["attention_backend"] = "skipped: no in-process model"
 
     if prefill:
         try:

@@ -54,7 +54,8 @@ def arms(tmp_path_factory):
 def test_engine_runs_the_plugin(arms):
     _, b = arms
     inst = b["engine"]["installed"]
-    for k in ("scheduler", "predictor", "swap", "decode_inputs", "sampler", "prefill"):
+    for k in ("scheduler", "predictor", "swap", "decode_inputs", "sampler", "prefill",
+              "attention_backend"):
         assert not inst[k].startswith("skipped"), (k, inst[k])
     s = b["summary"]
     assert s["finished"] == 40 and s["generated_tokens"] >= 40 * 64

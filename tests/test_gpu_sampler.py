@@ -121,3 +121,53 @@ def test_rejects_cpu_and_bad_layout():
         sample_rows(torch.zeros(2, 8))
     with pytest.raises(RuntimeError):
         sample_rows(torch.zeros(2, 8, device=DEV).t())
+
+
+def test_b200_sampler_general_path_on_gpu():
+    """Greedy requests with penalties / top-k / top-p / min-p / min_tokens / top-N logprobs through
+    B200Sampler with the real kernel, against the reference's own Sampler.forward on the same
+    GPU (reference package: oracle/_ref/vllm_py).  Greedy rows are deterministic: tokens, the
+    top-N token sets and ranks must match, log-probabilities to fp32 round-off."""
+    from tests import sched_replay as R
+    if not R.have_reference():
+        pytest.skip("reference package not shipped")
+    R.import_reference()
+    from vllm.model_executor.layers.sampler import Sampler
+    from vllm.model_executor.sampling_metadata import SamplingMetadata
+    from vllm.sampling_params import SamplingParams, SamplingType
+    from vllm.sequence import SequenceData
+
+    from vllm_ltr_b200.sampler import B200Sampler
+    vocab = 32000
+    specs = [dict(repetition_penalty=1.3, logprobs=3), dict(presence_penalty=0.7, frequency_penalty=0.2),
+             dict(top_k=17, logprobs=5), dict(top_p=0.6, logprobs=2), dict(min_p=0.05),
+             dict(min_tokens=4, logprobs=1), dict(), dict(top_k=1, top_p=0.5)] * 8
+    g = torch.Generator().manual_seed(3)
+    logits = (torch.randn(len(specs), vocab, generator=g) * 3).to(torch.float16).to(DEV)
+    seq_groups, seq_data = [], {}
+    cat = {t: [] for t in SamplingType}
+    for i, kw in enumerate(specs):
+        kw = dict(kw)
+        sp = SamplingParams(n=1, temperature=0.0, top_p=kw.pop("top_p", 1.0), max_tokens=16, **kw)
+        sp.eos_token_id = 2
+        seq_groups.append(([20 + i], sp))
+        sd = SequenceData([5, 6, 7, 5, int(logits[i].argmax())])
+        for t in (9, int(logits[i].argmax()), 11)[: 1 + i % 3]:
+            sd.append_token_id(t, 0.0)
+        seq_data[20 + i] = sd
+        cat[sp.sampling_type].append((i, len(cat[sp.sampling_type])))
+    cat = {t: (torch.tensor(v, dtype=torch.int, device=DEV) if v
+               else torch.empty(0, 2, dtype=torch.int, device=DEV)) for t, v in cat.items()}
+    md = SamplingMetadata(seq_groups, seq_data, [], torch.arange(len(specs), device=DEV), cat)
+    want = Sampler()(logits.clone(), md)
+    ours_s = B200Sampler()
+    got = ours_s(logits.clone(), md)
+    assert ours_s.general_steps == 1 and ours_s.reference_steps == 0
+    for a, b in zip(got.outputs, want.outputs):
+        sa, sb = a.samples[0], b.samples[0]
+        assert sa.output_token == sb.output_token
+        assert set(sa.logprobs) == set(sb.logprobs)
+        for t in sa.logprobs:
+            assert sa.logprobs[t].rank == sb.logprobs[t].rank
+            la, lb = sa.logprobs[t].logprob, sb.logprobs[t].logprob
+            assert la == lb or abs(la - lb) <= 2e-5 * max(1.0, abs(lb))

@@ -10,9 +10,12 @@ prompt/output token matrices on the host for penalties nobody asked for
 
 ``sample_rows``   tensor-level entry (tests, bench): tokens, logprobs, ranks for [rows, vocab] logits.
 ``B200Sampler``   drop-in for the engine: ``model.sampler = B200Sampler(reference=old_sampler)``;
-                  same ``forward`` signature and ``SamplerOutput``.  A step whose batch contains a
-                  request outside the subset is handed, whole, to the reference ``Sampler`` the
-                  engine was built with (counted in ``.reference_steps``); without one it raises
+                  same ``forward`` signature and ``SamplerOutput``.  Greedy / temperature steps
+                  are one kernel.  Steps with penalties, top-k / top-p / min-p, min_tokens or
+                  top-N logprobs first apply the reference's own logits edits, then the same
+                  kernel (``_forward_general``).  Beam search, best_of > 1, per-request seeds and
+                  prompt_logprobs hand the step, whole, to the reference ``Sampler`` the engine
+                  was built with (counted in ``.reference_steps``); without one it raises
                   ``NotImplementedError``.
 """
 import ctypes
@@ -93,25 +96,27 @@ class B200Sampler(torch.nn.Module):
 
     @staticmethod
     def _unsupported(i, sp, sampling_metadata) -> Optional[str]:
+        """Requests only the engine's own Sampler handles (the step is handed to it whole)."""
         from vllm.sampling_params import SamplingType
         if sp.sampling_type not in (SamplingType.GREEDY, SamplingType.RANDOM):
-            return f"sampling_type {sp.sampling_type!r}"
+            return f"sampling_type {sp.sampling_type!r}"     # beam search, per-request seeds
         if sp.prompt_logprobs is not None:
             return "prompt_logprobs"
-        if sp.logprobs is not None and sp.logprobs > 0:
-            return "logprobs > 0"
-        if sp.top_p < 1.0 - _SAMPLING_EPS or sp.top_k != -1 or sp.min_p > _SAMPLING_EPS:
-            return "top_p / top_k / min_p"
-        if (abs(sp.presence_penalty) >= _SAMPLING_EPS or abs(sp.frequency_penalty) >= _SAMPLING_EPS
-                or abs(sp.repetition_penalty - 1.0) >= _SAMPLING_EPS):
-            return "presence / frequency / repetition penalty"
-        if getattr(sp, "min_tokens", 0) > 0:
-            return "min_tokens"
-        if getattr(sp, "logits_processors", None):
-            return "logits_processors"
         if i < sampling_metadata.num_prompts and sp.best_of > 1:
             return "best_of > 1"
         return None
+
+    @staticmethod
+    def _needs_tensor_program(sp) -> bool:
+        """Penalties, top-k / top-p / min-p, min_tokens or top-N logprobs: the logits are first
+        edited by the reference's own tensor functions (sampler.py:104-224), then sampled by the
+        fused kernel; logprobs > 0 additionally materialises the fp32 log-prob matrix."""
+        return (sp.top_p < 1.0 - _SAMPLING_EPS or sp.top_k != -1 or sp.min_p > _SAMPLING_EPS
+                or abs(sp.presence_penalty) >= _SAMPLING_EPS
+                or abs(sp.frequency_penalty) >= _SAMPLING_EPS
+                or abs(sp.repetition_penalty - 1.0) >= _SAMPLING_EPS
+                or getattr(sp, "min_tokens", 0) > 0
+                or (sp.logprobs is not None and sp.logprobs > 0))
 
     def _staged(self, temps: List[float], rnd: List[int], device):
         """temperatures / random flags through one pinned buffer and one non-blocking copy."""
@@ -133,20 +138,25 @@ class B200Sampler(torch.nn.Module):
         assert logits is not None
         temps: List[float] = []
         rnd: List[int] = []
+        general = False
         for i, (seq_ids, sp) in enumerate(sampling_metadata.seq_groups):
             bad = self._unsupported(i, sp, sampling_metadata)
             if bad is not None:
                 if self.reference is None:
                     raise NotImplementedError(
-                        f"vllm_ltr_b200.B200Sampler handles greedy / temperature sampling only; "
-                        f"request uses {bad} - construct it with reference=<the engine's Sampler>")
+                        f"vllm_ltr_b200.B200Sampler does not sample requests with {bad}; "
+                        f"construct it with reference=<the engine's Sampler>")
                 self.reference_steps += 1
                 return self.reference(logits, sampling_metadata, pred_scores=pred_scores,
                                       aux_model_scores=aux_model_scores)
+            general = general or self._needs_tensor_program(sp)
             t = sp.temperature if sp.temperature >= _SAMPLING_EPS else 1.0   # sampling_metadata.py:133-137
             temps += [t] * len(seq_ids)
             rnd += [int(sp.sampling_type == SamplingType.RANDOM)] * len(seq_ids)
         assert len(temps) == logits.shape[0]
+        if general:
+            return self._forward_general(logits, sampling_metadata, rnd, pred_scores,
+                                         aux_model_scores)
         all_unit = all(t == 1.0 for t in temps)
         td = rd = None
         if not all_unit or any(rnd):
@@ -171,3 +181,59 @@ class B200Sampler(torch.nn.Module):
         return _build_sampler_output(results, sampling_metadata,
                                      [None] * len(sampling_metadata.seq_groups), sample_logprobs,
                                      pred_scores, aux_model_scores)
+
+    def _forward_general(self, logits, sampling_metadata, rnd, pred_scores, aux_model_scores):
+        """Steps with penalties / top-k / top-p / min-p / min_tokens / top-N logprobs.  The logits
+        edits are the reference's own functions, called in the reference's order (sampler.py:
+        47-75: min-tokens penalty, penalties, temperature, top-k/top-p, min-p); the softmax /
+        log-softmax / draw / rank that follow (sampler.py:77-90) are the fused kernel, and the
+        top-N dictionaries come from the reference's _get_logprobs over the kernel's fp32
+        log-prob matrix (only when some request asks for logprobs > 0)."""
+        from vllm.model_executor.layers import sampler as ref
+        from vllm.model_executor.sampling_metadata import SamplingTensors
+        from vllm.sequence import Logprob
+        self.general_steps = getattr(self, "general_steps", 0) + 1
+        _, vocab = logits.shape
+        logits = ref._apply_min_tokens_penalty(logits, sampling_metadata)
+        st, do_pen, do_topk, do_minp = SamplingTensors.from_sampling_metadata(
+            sampling_metadata, vocab, logits.device, logits.dtype)
+        if do_pen:
+            logits = ref._apply_penalties(logits, st.prompt_tokens, st.output_tokens,
+                                          st.presence_penalties, st.frequency_penalties,
+                                          st.repetition_penalties)
+        logits.div_(st.temperatures.unsqueeze_(dim=1))
+        if do_topk:
+            logits = ref._apply_top_k_top_p(logits, st.top_ps, st.top_ks)
+        if do_minp:
+            logits = ref._apply_min_p(logits, st.min_ps)
+        want_lp = any(sp.logprobs is not None and sp.logprobs > 0
+                      for _, sp in sampling_metadata.seq_groups)
+        rd = None
+        if any(rnd):
+            rd = torch.tensor(rnd, dtype=torch.uint8).to(logits.device, non_blocking=True)
+        if not logits.is_contiguous():
+            logits = logits.contiguous()
+        tokens, lps, ranks, _, lpf = sample_rows(logits, None, rd, seed=self.seed,
+                                                 offset=self.calls, want_logprobs=want_lp)
+        self.calls += 1
+        packed = torch.stack((tokens.to(torch.float64), lps.to(torch.float64),
+                              ranks.to(torch.float64))).cpu()
+        toks = packed[0].to(torch.int64).tolist()
+        lpl, rkl = packed[1].tolist(), packed[2].to(torch.int64).tolist()
+        results, row = [], 0
+        for seq_ids, _ in sampling_metadata.seq_groups:
+            n = len(seq_ids)
+            results.append((toks[row:row + n], list(range(n))))
+            row += n
+        if want_lp:
+            prompt_lp, sample_lp = ref._get_logprobs(lpf, sampling_metadata, results)
+        else:
+            prompt_lp = [None] * len(results)
+            sample_lp, row = [], 0
+            for seq_ids, _ in sampling_metadata.seq_groups:
+                n = len(seq_ids)
+                sample_lp.append([{toks[row + j]: Logprob(lpl[row + j], rkl[row + j])}
+                                  for j in range(n)])
+                row += n
+        return ref._build_sampler_output(results, sampling_metadata, prompt_lp, sample_lp,
+                                         pred_scores, aux_model_scores)

@@ -43,6 +43,7 @@ attntrace) stage "attention timeline (trace build)"
   VLTR_LIB=$PWD/vllm_ltr_b200/libvllm_ltr_b200_trace.so timeout 600 python tools/attn_tune.py --trace --cases ${ATTN_CASES:-70b-tp8-bf16:256:trace,7b-tp8-bf16:256:trace} > $O/attn_trace.log 2>&1; echo "rc=$?" | tee -a $O/session2.log
   VLTR_PDL=0 VLTR_LIB=$PWD/vllm_ltr_b200/libvllm_ltr_b200_trace.so timeout 600 python tools/attn_tune.py --trace --cases 70b-tp8-bf16:256:trace >> $O/attn_trace.log 2>&1
   cat $O/attn_trace.log;;
+ipc) stage "ipc probe"; timeout 120 python tools/ipc_probe.py > $O/ipc_probe.log 2>&1; cat $O/ipc_probe.log | tail -5;;
 esac
 done
 stage done

@@ -10,7 +10,16 @@ the ragged tables are converted once (one ``np.fromiter`` over all block ids) an
 the padded array with a mask; the per-sequence Python loop only reads what it must from the
 ``SequenceData`` objects.
 
-``install(model_runner)`` re-binds ``_prepare_decode`` on a reference ``ModelRunner``.
+``prepare_prompt`` is the same for the prefill chunks of a step (``ModelRunner._prepare_prompt``,
+model_runner.py:224-422) in the configuration the LTR engine runs - chunked prefill, no LoRA, no
+multi-modal input, no prefix caching, no sliding window; anything else is handed to the
+reference method.  The reference walks every chunk token in Python to compute its slot and
+creates six small device tensors one blocking copy at a time plus two cumsum launches; here
+positions and slots of a chunk are two numpy expressions, the prefix sums are computed on the
+host, and all int32 metadata of the step crosses to the device in ONE copy (block tables,
+context lengths and both start-offset vectors are views of it).
+
+``install(model_runner)`` re-binds both on a reference ``ModelRunner``.
 """
 import types
 from itertools import chain
@@ -114,7 +123,73 @@ def prepare_decode(self, seq_group_metadata_list):
         lora_requests=lora_requests, slot_mapping=slot_mapping)
 
 
+def prepare_prompt(self, seq_group_metadata_list):
+    M = _ref()
+    mds = seq_group_metadata_list
+    if len(mds) == 0:
+        return M.PreparePromptMetadata.empty()
+    chunked = self.scheduler_config is not None and self.scheduler_config.chunked_prefill_enabled
+    plain = chunked and self.sliding_window is None and all(
+        md.lora_int_id == 0 and not md.multi_modal_data and not md.computed_block_nums
+        and md.block_tables is not None and len(md.seq_data) == 1 for md in mds)
+    if not plain:        # profiling run, LoRA, images, prefix caching, sliding window: reference
+        return self._vltr_ref_prepare_prompt(mds)
+    bs = self.block_size
+    n = len(mds)
+    tokens: List[int] = []
+    pos_parts, slot_parts, tables = [], [], []
+    ctx = np.empty(n, dtype=np.int64)          # tokens already computed (the prefix)
+    end = np.empty(n, dtype=np.int64)          # prefix + this chunk
+    for i, md in enumerate(mds):
+        assert md.is_prompt
+        (seq_id, data), = md.seq_data.items()
+        c = data.get_num_computed_tokens()
+        e = min(data.get_len(), c + md.token_chunk_size)
+        ctx[i], end[i] = c, e
+        tokens.extend(data.get_token_ids()[c:e])
+        table = md.block_tables[seq_id]
+        tables.append(table)
+        p = np.arange(c, e, dtype=np.int64)
+        pos_parts.append(p)
+        # slot of chunk token at position p: its block's id * block size + offset in the block
+        slot_parts.append(np.asarray(table, dtype=np.int64)[p // bs] * bs + p % bs)
+    sub = end - ctx
+    assert int(sub.max()) > 0
+    width = max(len(t) for t in tables)
+    # one int32 staging array: [block tables | context lens | subquery starts | sequence starts]
+    nbt = n * width
+    stage = np.zeros(nbt + n + 2 * (n + 1), dtype=np.int32)
+    if width:
+        _padded_tables(tables, stage[:nbt].reshape(n, width))
+    stage[nbt:nbt + n] = ctx
+    np.cumsum(sub, out=stage[nbt + n + 1:nbt + 2 * n + 1])
+    np.cumsum(end, out=stage[nbt + 2 * n + 2:])
+    dev = torch.from_numpy(stage).to(self.device)
+    prompt_lens = end.tolist()
+    attn_metadata = self.attn_backend.make_metadata(
+        is_prompt=True, prompt_lens=prompt_lens,
+        prompt_lens_tensor=torch.from_numpy(end).to(self.device), max_subquery_len=int(sub.max()),
+        max_context_len=None, max_prompt_len=int(end.max()),
+        subquery_start_loc=dev[nbt + n:nbt + 2 * n + 1], seq_start_loc=dev[nbt + 2 * n + 1:],
+        context_lens=dev[nbt:nbt + n], block_tables=dev[:nbt].view(n, width),
+        use_cuda_graph=False)
+    ntok = len(tokens)
+    return M.PreparePromptMetadata(
+        input_tokens=tokens, input_positions=np.concatenate(pos_parts).tolist(),
+        attn_metadata=attn_metadata, prompt_lens=prompt_lens, subquery_lens=sub.tolist(),
+        lora_index_mapping=[0] * ntok,
+        lora_prompt_mapping=[0] * sum(int(sub[i]) if md.sampling_params.prompt_logprobs else 1
+                                      for i, md in enumerate(mds)),
+        lora_requests=set(),
+        multi_modal_input=None, slot_mapping=np.concatenate(slot_parts).tolist())
+
+
 def install(model_runner):
-    """Bind the fast ``_prepare_decode`` on a reference ``ModelRunner``."""
+    """Bind the fast ``_prepare_decode`` / ``_prepare_prompt`` on a reference ``ModelRunner``."""
     model_runner._prepare_decode = types.MethodType(prepare_decode, model_runner)
+    ref_prompt = getattr(model_runner, "_prepare_prompt", None)
+    if ref_prompt is not None:
+        if not hasattr(model_runner, "_vltr_ref_prepare_prompt"):
+            model_runner._vltr_ref_prepare_prompt = ref_prompt
+        model_runner._prepare_prompt = types.MethodType(prepare_prompt, model_runner)
     return model_runner

@@ -85,7 +85,8 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
         if decode_inputs:
             from . import decode_inputs as mr
             mr.install(runner)
-            done["decode_inputs"] = "ModelRunner._prepare_decode: vectorised builder"
+            done["decode_inputs"] = ("ModelRunner._prepare_decode / _prepare_prompt: vectorised "
+                                     "builders, one metadata copy per step")
         if sampler:
             model = getattr(runner, "model", None)
             if model is not None and hasattr(model, "sampler"):

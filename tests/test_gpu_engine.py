@@ -91,5 +91,8 @@ def test_engine_predictor_scores_agree(arms):
     a, b = arms
     p = compare(a, b, TIE_TOL)["predictor"]
     assert p["n"] == 40
-    assert p["max_abs_diff"] <= 2e-2, p       # fp16 logits
+    # stated tolerance: each side is an fp16 forward within 2e-2 of the float64 restatement
+    # (tests/test_gpu_predictor.py for ours) - the reference's flash-attn / cuBLAS pipeline rounds
+    # differently from ours, so the two can be up to twice that apart; the ORDER must agree
+    assert p["max_abs_diff"] <= 4e-2, p
     assert p["kendall_tau"] >= 0.99, p

@@ -50,9 +50,9 @@ class RefCustomAllreduce:
 
     def _ipc(self, t):
         data = t.untyped_storage()._share_cuda_()
-        handle = bytes(data[1])
-        if len(handle) == 65:        # torch >= 2.5 prefixes the cudaIpcMemHandle_t with a type byte
-            handle = handle[1:]
+        # torch >= 2.5 prefixes the 64-byte cudaIpcMemHandle_t with version / type bytes (66 bytes
+        # on torch 2.11, tools/ipc_probe.py): the driver handle is the tail
+        handle = bytes(data[1])[-64:]
         allv = [None] * self.world
         dist.all_gather_object(allv, (handle, data[3]))
         return [a[0] for a in allv], [a[1] for a in allv]

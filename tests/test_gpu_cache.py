@@ -121,6 +121,73 @@ def test_reshape_and_cache_engine_shapes(cache_ops, num_tokens, heads, dtype, kv
     assert torch.equal(ks[0].cpu(), rk) and torch.equal(vs[0].cpu(), rv)
 
 
+def _run_slots(rnd, bs, nb):
+    """Slot mapping of a mixed engine step: prefill chunks (runs of consecutive slots that start
+    and end anywhere inside a block and continue in unrelated blocks), padding inside a run,
+    a descending pair, a run broken by one slot, then lone decode tokens."""
+    blocks = rnd.sample(range(nb), 64)
+    slots = []
+    for start, length in ((0, 3 * bs), (bs - 3, bs + 5), (5, 2), (bs - 1, 1), (1, 4 * bs - 2)):
+        pos = start
+        for _ in range(length):
+            slots.append(blocks[pos // bs] * bs + pos % bs)
+            pos += 1
+        blocks = blocks[8:]
+    b = blocks[0] * bs
+    slots += [b + 2, b + 3, -1, b + 5, b + 6]            # padding token inside a run
+    b = blocks[1] * bs
+    slots += [b + 7, b + 6, b + 5]                       # descending: three runs of one
+    b = blocks[2] * bs
+    slots += [b, b + 1, b + 3, b + 4, b + 4 + bs]        # a gap, then the same offset one block on
+    slots += [blk * bs + rnd.randrange(bs) for blk in blocks[3:20]]
+    return slots
+
+
+@pytest.mark.parametrize("block_size", BLOCK_SIZES)
+@pytest.mark.parametrize("head_size", [64, 80, 128])
+@pytest.mark.parametrize("heads,dtype,kv", [(32, torch.half, "auto"), (8, torch.bfloat16, "auto"),
+                                             (8, torch.bfloat16, "fp8"), (8, torch.half, "fp8"),
+                                             (2, torch.float, "auto"), (2, torch.float, "fp8")])
+def test_reshape_and_cache_runs(cache_ops, block_size, head_size, heads, dtype, kv):
+    """Tokens with consecutive slots inside a block are written by one warp with wide stores
+    (csrc/cache.cu): every way a run can start, end and break must give the reference's bytes."""
+    rnd = random.Random(7)
+    nb, hq = 512, 4
+    slots_l = _run_slots(rnd, block_size, nb)
+    T = len(slots_l)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    qkv = torch.randn(T, (hq + 2 * heads) * head_size, generator=g, device=DEV).to(dtype)
+    key = qkv[:, hq * head_size:(hq + heads) * head_size].view(T, heads, head_size)
+    value = qkv[:, (hq + heads) * head_size:].view(T, heads, head_size)
+    slots = torch.tensor(slots_l, dtype=torch.long, device=DEV)
+    ks, vs = _caches(nb, block_size, 1, heads, head_size, dtype, kv, 7)
+    rk, rv = ks[0].cpu(), vs[0].cpu()
+    cache_ops.reshape_and_cache(key, value, ks[0], vs[0], slots, kv, 1.0)
+    K.reshape_and_cache(key.cpu(), value.cpu(), rk, rv, slots.cpu(), kv)
+    assert torch.equal(ks[0].cpu(), rk) and torch.equal(vs[0].cpu(), rv)
+
+
+def test_reshape_and_cache_prefill_step(cache_ops):
+    """A 768-token engine step: two prompt chunks and 200 decode tokens, Llama-2-7B heads."""
+    rnd = random.Random(9)
+    D, bs, nb, H = 128, 16, 4096, 32
+    blocks = rnd.sample(range(nb), 300)
+    slots_l = [blocks[i // bs] * bs + i % bs for i in range(400)]                  # new prompt
+    slots_l += [blocks[40 + (9 + i) // bs] * bs + (9 + i) % bs for i in range(168)]  # continued
+    slots_l += [blocks[100 + i] * bs + rnd.randrange(bs) for i in range(200)]      # decode
+    T = len(slots_l)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    qkv = torch.randn(T, 3 * H * D, generator=g, device=DEV).to(torch.half)
+    key = qkv[:, H * D:2 * H * D].view(T, H, D)
+    value = qkv[:, 2 * H * D:].view(T, H, D)
+    slots = torch.tensor(slots_l, dtype=torch.long, device=DEV)
+    ks, vs = _caches(nb, bs, 1, H, D, torch.half, "auto", 9)
+    rk, rv = ks[0].cpu(), vs[0].cpu()
+    cache_ops.reshape_and_cache(key, value, ks[0], vs[0], slots, "auto", 1.0)
+    K.reshape_and_cache(key.cpu(), value.cpu(), rk, rv, slots.cpu(), "auto")
+    assert torch.equal(ks[0].cpu(), rk) and torch.equal(vs[0].cpu(), rv)
+
+
 @pytest.mark.parametrize("direction", [("cuda", "cpu"), ("cuda", "cuda"), ("cpu", "cuda")])
 @pytest.mark.parametrize("head_size", [64, 80, 128, 256])
 @pytest.mark.parametrize("block_size", BLOCK_SIZES)

@@ -84,6 +84,10 @@ struct Params {
 #ifndef VLTR_ATTN_TRACE
 #define VLTR_ATTN_TRACE 0
 #endif
+// two interleaved accumulator chains for S^T = K.Q^T (tensor-core path)
+#ifndef VLTR_ATTN_SPLIT_QK
+#define VLTR_ATTN_SPLIT_QK 1
+#endif
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -184,6 +188,15 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
+}
+
+// 2^x on the SFU, flush-to-zero: one MUFU.EX2.  exp2f() wraps the same instruction in a range
+// fix-up for results below 2^-126 (compare, halve, square: 3 more instructions per call); softmax
+// weights that small round to zero in the f16 / bf16 operand anyway.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 template <typename MT>
@@ -677,6 +690,14 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
   const int v_row = lane / (C::LPR > 0 ? C::LPR : 1), v_sub = lane % (C::LPR > 0 ? C::LPR : 1);
   // lane geometry (MMA path): g = row of the 16 x 8 fragment, t4 = column pair
   const int g = lane >> 2, t4 = lane & 3;
+  // e5m2 tensor-core path, block size >= 16: row r of a 16-token M tile of S^T = K.Q^T holds token
+  //   r = 2t + e      (r < 8)  -> 4t + e          r = 8 + 2t + e  -> 4t + 2 + e      (t = 0..3, e = 0,1)
+  // so that after the movmatrix transpose the k slots {2t4, 2t4+1, 2t4+8, 2t4+9} of P^T are the
+  // CONSECUTIVE tokens 4t4 .. 4t4+3 - four adjacent bytes of a V row.  prow0 = token of row g,
+  // prow0 + prow8 = token of row g + 8.  Everything else keeps the identity (prow0 = g, prow8 = 8).
+  constexpr bool PERM = MMA && C::FP8 && BS >= 16;
+  const int prow0 = PERM ? 4 * (g >> 1) + (g & 1) : g;
+  constexpr int prow8 = PERM ? 2 : 8;
 
   int stage_c = 0;        // consumer cursor over the ring (continues across items)
   uint32_t phase_c = 0;
@@ -874,6 +895,18 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
         for (int mt = 0; mt < MTL; ++mt)
 #pragma unroll
           for (int nh = 0; nh < NH; ++nh) st[mt][nh][0] = st[mt][nh][1] = st[mt][nh][2] = st[mt][nh][3] = 0.f;
+        // the KS products of a tile accumulate into the same registers: a dependent chain of KS
+        // tensor-core latencies per warp.  SPLIT_QK keeps a second accumulator for the odd
+        // k-steps (two chains of KS / 2) and adds them at the end.
+        constexpr bool SPLIT_QK = VLTR_ATTN_SPLIT_QK && C::KS >= 4 && C::KS % 2 == 0;
+        float st2[SPLIT_QK ? MTL : 1][SPLIT_QK ? NH : 1][4];
+        if constexpr (SPLIT_QK) {
+#pragma unroll
+          for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+            for (int nh = 0; nh < NH; ++nh)
+              st2[mt][nh][0] = st2[mt][nh][1] = st2[mt][nh][2] = st2[mt][nh][3] = 0.f;
+        }
 #pragma unroll
         for (int ks = 0; ks < C::KS; ++ks) {
 #pragma unroll
@@ -892,12 +925,14 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
               }
             } else {
               // e5m2 K tile [D/16][BS][16]: bytes 4t4..4t4+3 of (k-step ks, token) are this
-              // thread's four k slots
-              const uint32_t w0 = lds4(ktile + ((ks * BS + 16 * mt + g) << 4) + 4 * t4);
+              // thread's four k slots.  Which token sits in which row of the M tile is free
+              // (the softmax runs down the rows, P^T inherits the order): rows g and g + 8 take
+              // tokens prow0 and prow0 + 2 (see PERM above) so that V needs one load per row.
+              const uint32_t w0 = lds4(ktile + ((ks * BS + 16 * mt + prow0) << 4) + 4 * t4);
               a[0] = __byte_perm(w0, 0, 0x1404);
               a[2] = __byte_perm(w0, 0, 0x3424);
               if constexpr (BS >= 16) {
-                const uint32_t w1 = lds4(ktile + ((ks * BS + 16 * mt + 8 + g) << 4) + 4 * t4);
+                const uint32_t w1 = lds4(ktile + ((ks * BS + 16 * mt + prow0 + prow8) << 4) + 4 * t4);
                 a[1] = __byte_perm(w1, 0, 0x1404);
                 a[3] = __byte_perm(w1, 0, 0x3424);
               } else {
@@ -906,8 +941,21 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
               }
             }
 #pragma unroll
-            for (int nh = 0; nh < NH; ++nh) mma16816<MT>(st[mt][nh], a, qa[ks][nh], qa[ks][2 + nh]);
+            for (int nh = 0; nh < NH; ++nh) {
+              if (SPLIT_QK && (ks & 1))
+                mma16816<MT>(st2[mt][nh], a, qa[ks][nh], qa[ks][2 + nh]);
+              else
+                mma16816<MT>(st[mt][nh], a, qa[ks][nh], qa[ks][2 + nh]);
+            }
           }
+        }
+        if constexpr (SPLIT_QK) {
+#pragma unroll
+          for (int mt = 0; mt < MTL; ++mt)
+#pragma unroll
+            for (int nh = 0; nh < NH; ++nh)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) st[mt][nh][i] += st2[mt][nh][i];
         }
         // ---- online softmax down the token rows of each head column (log2 domain) --------------
         // only the context's last block can hold out-of-context tokens, and ALiBi is rare: the
@@ -927,7 +975,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
               for (int hh = 0; hh < 2; ++hh) {
                 float sv = st[mt][nh][2 * hh + e] * scale_l2;
                 if (!plain) {
-                  const int row = 16 * mt + 8 * hh + g;
+                  const int row = 16 * mt + prow8 * hh + prow0;
                   const int tok = tok0 + row;
                   sv += slope[c] * (float)(tok - ctx + 1);
                   sv = (tok < ctx && row < BS) ? sv : -INFINITY;
@@ -943,7 +991,7 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
             // the running maximum settles after the first tiles: rescale only when some head's
             // maximum moved (warp-uniform; alpha == 1 exactly otherwise)
             if (__any_sync(0xffffffffu, m_new[e] != m[c])) {
-              const float alpha = exp2f(m[c] - m_new[e]);
+              const float alpha = ex2_ftz(m[c] - m_new[e]);
               m[c] = m_new[e];
               l[c] *= alpha;
 #pragma unroll
@@ -960,8 +1008,8 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
               if (BS >= 16 || hh == 0) {
                 // (token row, heads 2t4 and 2t4+1) packed, rounded to the operand type; the row
                 // sums use the rounded weights, like the products do
-                const uint32_t pk = pack2<MT>(exp2f(st[mt][nh][2 * hh] - m_new[0]),
-                                              exp2f(st[mt][nh][2 * hh + 1] - m_new[1]));
+                const uint32_t pk = pack2<MT>(ex2_ftz(st[mt][nh][2 * hh] - m_new[0]),
+                                              ex2_ftz(st[mt][nh][2 * hh + 1] - m_new[1]));
                 const float2 pf = unpack2<MT>(pk);
                 l[2 * nh] += pf.x;
                 l[2 * nh + 1] += pf.y;
@@ -992,19 +1040,27 @@ __global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_const
                 a[3] = 0u;
               }
             } else {
-              // e5m2 V tile [D][BS] bytes: two 16-bit loads per (row, half of the token step)
-              const uint32_t row0 = vtile + (16 * dt + g) * BS + 16 * mt + 2 * t4;
-              uint32_t w0, w1, w2 = 0, w3 = 0;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w0) : "r"(row0));
-              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w1) : "r"(row0 + 8 * BS));
-              if constexpr (BS >= 16) {
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w2) : "r"(row0 + 8));
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w3) : "r"(row0 + 8 * BS + 8));
+              if constexpr (PERM) {
+                // e5m2 V tile [D][BS] bytes.  With the token rows of S^T permuted, the P^T
+                // fragments carry tokens 4t4, 4t4+1 (k slots 2t4, 2t4+1) and 4t4+2, 4t4+3 (k slots
+                // 2t4+8, 2t4+9): the four V bytes of a row are ONE 32-bit load
+                const uint32_t row0 = vtile + (16 * dt + g) * BS + 16 * mt + 4 * t4;
+                const uint32_t w0 = lds4(row0), w1 = lds4(row0 + 8 * BS);
+                a[0] = __byte_perm(w0, 0, 0x1404);
+                a[1] = __byte_perm(w1, 0, 0x1404);
+                a[2] = __byte_perm(w0, 0, 0x3424);
+                a[3] = __byte_perm(w1, 0, 0x3424);
+              } else {
+                // block size 8: two 16-bit loads (tokens 2t4, 2t4+1 of rows g, g + 8)
+                const uint32_t row0 = vtile + (16 * dt + g) * BS + 16 * mt + 2 * t4;
+                uint32_t w0, w1;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w0) : "r"(row0));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w1) : "r"(row0 + 8 * BS));
+                a[0] = __byte_perm(w0, 0, 0x1404);
+                a[1] = __byte_perm(w1, 0, 0x1404);
+                a[2] = 0u;
+                a[3] = 0u;
               }
-              a[0] = __byte_perm(w0, 0, 0x1404);
-              a[1] = __byte_perm(w1, 0, 0x1404);
-              a[2] = __byte_perm(w2, 0, 0x1404);
-              a[3] = __byte_perm(w3, 0, 0x1404);
             }
 #pragma unroll
             for (int nh = 0; nh < NH; ++nh)

@@ -9,10 +9,12 @@
 //   value_cache [num_blocks, num_kv_heads, head_size, block_size]
 //
 // B200 shape:
-//   reshape_and_cache — one warp per (token, head) row flattened over the grid; each K chunk is
-//     read with 128-bit loads and written with ONE 16-byte store (the layout keeps x elements of
-//     a token together), V is scalar stores with lanes on consecutive head elements (the layout
-//     strides a token's elements by block_size: one 32-byte sector per element).
+//   reshape_and_cache — one warp per (token, head) row flattened over the grid; tokens whose slots
+//     are consecutive inside a KV block (every prefill chunk) are written by the warp of the run's
+//     first token: K as 16-byte pieces that fill whole lines, V as 16-byte pieces of the
+//     block_size-token rows (full sectors).  A lone token (decode) keeps one 16-byte store per K
+//     chunk and one element store per V row (the layout strides a token's elements by
+//     block_size: one 32-byte sector per element, inherent).
 //   copy_blocks — layer pointers and (src,dst) pairs travel as kernel parameters (CUDA >= 12.1
 //     allows 32 KB of them): no pointer-array tensors, no blocking H2D copies (the reference does
 //     three per call, cache_kernels.cu:129-136), 128-bit copies, grid sized over
@@ -35,53 +37,86 @@ __device__ __forceinline__ CT cache_cvt(T v) {
     return v;
 }
 
-// vector path: one warp per (token, head) row.
-//   K: the layout keeps x = XE consecutive head elements of a token together, so lane c moves
-//      chunk c with 128-bit loads and ONE 128-bit store.
-//   V: the layout strides a token's elements by block_size, every element lands in its own
-//      32-byte sector (read-modify-write in DRAM - inherent to the layout).  Lanes take
-//      CONSECUTIVE head elements, so one store instruction touches 32 sectors that are
-//      block_size*sizeof(CT) bytes apart (8 or fewer 128-byte lines) instead of 32 lines.
+// vector path: one warp per (token, head) row; the warp of the FIRST token of a run does the work.
+//   A run = consecutive tokens whose slots are consecutive inside one KV block - what every
+//   prefill chunk produces (block_size tokens per block), while decode tokens are runs of one.
+//   The paged layouts keep the tokens of a block adjacent (K: 16-byte chunks of consecutive
+//   tokens follow each other; V: the block_size tokens of one head element are one contiguous
+//   row), so a run turns the scatter into wide stores:
+//   K: (chunk, token) pairs over the lanes, consecutive lanes -> consecutive tokens of a chunk:
+//      128-bit loads, 128-bit stores that fill whole lines.
+//   V: lanes on consecutive head elements; each lane gathers its element from the run's tokens
+//      and stores 16 bytes at a time where the run covers an aligned 16-byte group - full 32-byte
+//      sectors instead of one read-modify-write sector per element (the single-token case keeps
+//      the element stores: inherent to the layout).
 template <typename T, typename CT, bool FP8>
 __global__ void __launch_bounds__(256)
     reshape_and_cache_vec_kernel(const T* __restrict__ key, const T* __restrict__ value,
                                  CT* __restrict__ key_cache, CT* __restrict__ value_cache,
                                  const int64_t* __restrict__ slot_mapping, int64_t key_stride,
                                  int64_t value_stride, int num_heads, int head_size,
-                                 int block_size, int64_t num_rows) {
-  constexpr int XE = 16 / sizeof(CT);              // == x
+                                 int block_size, int64_t num_rows, int num_tokens) {
+  constexpr int XE = 16 / sizeof(CT);              // == x, also tokens per 16 bytes of a V row
   constexpr int LD = XE * sizeof(T) / 16;          // 16-byte loads per K chunk
   constexpr int N = 16 / sizeof(T);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  // the slot mapping is a step input (host-built, copied in before the layer loop): its load
-  // overlaps the tail of the kernel that produced key / value
+  // the slot mapping is a step input (host-built, copied in before the layer loop): its loads
+  // overlap the tail of the kernel that produced key / value
   const int64_t token = row < num_rows ? row / num_heads : 0;
-  const int64_t slot = row < num_rows ? slot_mapping[token] : -1;
+  int64_t slot = -1, prev = -2;
+  int n = 0;
+  if (row < num_rows) {
+    slot = slot_mapping[token];
+    if (token > 0) prev = slot_mapping[token - 1];
+    // run length: following tokens with consecutive slots, up to the end of the block
+    const int room = block_size - (int)(slot % block_size);
+    const bool cont = lane > 0 && lane < room && token + lane < num_tokens &&
+                      slot_mapping[token + lane] == slot + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, cont || lane == 0);
+    n = __ffs(~m) - 1;                             // leading ones (lane 0 always set); 32 -> -1
+    if (n < 0) n = 32;
+    if (n > room) n = room;
+  }
   pdl_wait();
   pdl_trigger();
-  if (row >= num_rows) return;
-  const int head = (int)(row % num_heads);
-  if (slot < 0) return;  // padding token (cache_kernels.cu:172-175)
-  const int64_t blk = slot / block_size;
+  if (row >= num_rows || slot < 0) return;         // padding token (cache_kernels.cu:172-175)
   const int off = (int)(slot % block_size);
+  if (prev >= 0 && prev == slot - 1 && off != 0) return;   // inside a run: its first token's warp writes it
+  const int head = (int)(row % num_heads);
+  const int64_t blk = slot / block_size;
   const int chunks = head_size / XE;
   const int64_t bh = blk * num_heads + head;
   const T* ksrc = key + token * key_stride + (int64_t)head * head_size;
   const T* vsrc = value + token * value_stride + (int64_t)head * head_size;
-  // V first: its scattered stores are the long pole, get them in flight early
-  CT* vdst = value_cache + bh * head_size * block_size + off;
-  for (int d = lane; d < head_size; d += 32)
-    vdst[(int64_t)d * block_size] = cache_cvt<T, CT, FP8>(vsrc[d]);
-  for (int chunk = lane; chunk < chunks; chunk += 32) {
+  // V first: its stores are the long pole, get them in flight early
+  for (int d = lane; d < head_size; d += 32) {
+    CT* vrow = value_cache + (bh * head_size + d) * block_size;
+    for (int e0 = (off / XE) * XE; e0 < off + n; e0 += XE) {
+      if (e0 >= off && e0 + XE <= off + n) {       // the run covers this aligned 16-byte group
+        alignas(16) CT buf[XE];
+#pragma unroll
+        for (int e = 0; e < XE; ++e)
+          buf[e] = cache_cvt<T, CT, FP8>(vsrc[(int64_t)(e0 - off + e) * value_stride + d]);
+        st_16(vrow + e0, *reinterpret_cast<uint4*>(buf));
+      } else {
+        const int lo = e0 > off ? e0 : off, hi = e0 + XE < off + n ? e0 + XE : off + n;
+        for (int e = lo; e < hi; ++e)
+          vrow[e] = cache_cvt<T, CT, FP8>(vsrc[(int64_t)(e - off) * value_stride + d]);
+      }
+    }
+  }
+  for (int idx = lane; idx < chunks * n; idx += 32) {
+    const int chunk = idx / n, i = idx - chunk * n;
     alignas(16) T kbuf[XE];
 #pragma unroll
     for (int l = 0; l < LD; ++l)
-      *reinterpret_cast<uint4*>(&kbuf[l * N]) = ld_nc_16(ksrc + chunk * XE + l * N);
+      *reinterpret_cast<uint4*>(&kbuf[l * N]) =
+          ld_nc_16(ksrc + (int64_t)i * key_stride + chunk * XE + l * N);
     alignas(16) CT kout[XE];
 #pragma unroll
     for (int e = 0; e < XE; ++e) kout[e] = cache_cvt<T, CT, FP8>(kbuf[e]);
-    CT* kdst = key_cache + ((bh * chunks + chunk) * block_size + off) * XE;
+    CT* kdst = key_cache + ((bh * chunks + chunk) * block_size + off + i) * XE;
     st_16(kdst, *reinterpret_cast<uint4*>(kout));
   }
 }
@@ -122,12 +157,14 @@ int launch_reshape(const void* key, const void* value, void* key_cache, void* va
   if (num_tokens == 0 || num_heads == 0 || head_size == 0) return VLTR_OK;
   const bool vec_ok = x == XE && head_size % XE == 0 && key_stride % N == 0 &&
                       value_stride % N == 0 && (uintptr_t)key % 16 == 0 &&
-                      (uintptr_t)value % 16 == 0 && (uintptr_t)key_cache % 16 == 0;
+                      (uintptr_t)value % 16 == 0 && (uintptr_t)key_cache % 16 == 0 &&
+                      (uintptr_t)value_cache % 16 == 0 && block_size % XE == 0 && block_size <= 32;
   if (vec_ok) {
     const int64_t rows = (int64_t)num_tokens * num_heads;
     launch(reshape_and_cache_vec_kernel<T, CT, FP8>, dim3((unsigned)((rows + 7) / 8)), dim3(256),
            0, stream, (const T*)key, (const T*)value, (CT*)key_cache, (CT*)value_cache,
-           slot_mapping, key_stride, value_stride, num_heads, head_size, block_size, rows);
+           slot_mapping, key_stride, value_stride, num_heads, head_size, block_size, rows,
+           num_tokens);
   } else {
     const int64_t items = (int64_t)num_tokens * num_heads * head_size;
     reshape_and_cache_scalar_kernel<T, CT, FP8>

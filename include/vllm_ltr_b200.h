@@ -223,9 +223,22 @@ int vltr_opt_forward(const void* handle, const int32_t* token_ids, const int32_t
                      float* logits, void* stream);
 /* The dense layer the predictor is built from, exposed for tests:
  * D[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + resid[M,N]  (tcgen05.mma, fp32 accumulate in TMEM;
- * bias / resid may be NULL; N % 64 == 0, K % 8 == 0; dtype f16 / bf16). */
+ * bias / resid may be NULL; N % 8 == 0, K % 8 == 0; dtype f16 / bf16). */
 int vltr_opt_gemm(const void* A, const void* W, void* D, const void* bias, const void* resid, int M,
                   int N, int K, int relu, int dtype, void* stream);
+
+/* ---- lm_head logits (f3, first half) -------------------------------------------------------------
+ * Replaces the matmul of LogitsProcessor._get_logits
+ * (vllm/model_executor/layers/logits_processor.py:61-64: `torch.matmul(hidden_states,
+ * embedding.t())` + optional bias) for the rows _prune_hidden_states selected (:73-78).
+ *   logits[num_rows, vocab_rows] = hidden[num_rows, hidden_size] . weight[vocab_rows, hidden_size]^T
+ *                                  (+ bias[vocab_rows])
+ * all row-major and contiguous, f16 / bf16, fp32 accumulation in TMEM, ONE rounding of the result
+ * (the reference rounds the product, then the sum with the bias).  vocab_rows is the rank's
+ * shard of the (padded) vocabulary and only needs to be a multiple of 8; hidden_size % 8 == 0.
+ * The tensor-parallel gather (:65) and the vocabulary trim (:67-68) stay with the caller. */
+int vltr_lm_head_logits(const void* hidden, const void* weight, const void* bias, void* logits,
+                        int num_rows, int vocab_rows, int hidden_size, int dtype, void* stream);
 
 /* ---- tensor-parallel exchange (config 5: 70B at TP=8) ------------------------------------------
  * Replaces tensor_model_parallel_all_reduce (vllm/distributed/communication_op.py:13-42; reference

@@ -26,7 +26,9 @@ def P():
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("m", [1, 7, 128, 129, 300, 2048])
 @pytest.mark.parametrize("n,k", [(2304, 768), (768, 768), (3072, 768), (768, 3072), (1024, 512),
-                                 (512, 1024), (64, 64), (4096, 1024)])
+                                 (512, 1024), (64, 64), (4096, 1024),
+                                 # partial last column tile (vocabulary shards of the lm_head)
+                                 (4000, 512), (200, 64), (72, 128), (8, 64)])
 def test_dense_layer(P, dtype, m, n, k):
     g = torch.Generator(device=DEV).manual_seed(m * 7 + n + k)
     a = torch.randn(m, k, generator=g, device=DEV).to(dtype)
@@ -51,7 +53,7 @@ def test_dense_layer(P, dtype, m, n, k):
 
 def test_dense_layer_errors(P):
     a = torch.zeros(4, 64, dtype=torch.float16, device=DEV)
-    with pytest.raises(RuntimeError, match="multiple of 64"):
+    with pytest.raises(RuntimeError, match="multiples of 8"):
         P.gemm(a, torch.zeros(100, 64, dtype=torch.float16, device=DEV))
     with pytest.raises(RuntimeError, match="Unsupported data type"):
         P.gemm(a.float(), torch.zeros(64, 64, device=DEV))

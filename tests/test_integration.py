@@ -82,3 +82,61 @@ def test_attention_backend_seam(monkeypatch):
                              kv_cache_dtype="auto", slot_mapping=torch.zeros(1, dtype=torch.long),
                              num_prefill_tokens=0, num_decode_tokens=1, prefill_metadata=None,
                              decode_metadata=None), 1.0)
+
+
+def test_logits_processor_seam(monkeypatch):
+    """f3 (logits half): ``logits.install`` re-binds ``LogitsProcessor._get_logits``; the host
+    logic around the matmul (bias, gather, vocabulary trim, None on non-driver ranks) is the
+    reference's.  The kernel call is replaced by a torch matmul here (no GPU)."""
+    import torch
+    R.import_reference()
+    import vllm.distributed as vd
+    import vllm.model_executor.layers.logits_processor as ref_lp
+
+    from vllm_ltr_b200 import integration, logits as lg
+
+    monkeypatch.setattr(ref_lp, "tensor_model_parallel_gather", lambda x: x)
+    monkeypatch.setattr(vd, "tensor_model_parallel_gather", lambda x: x)
+    calls = []
+
+    def fake(hidden, emb, bias=None):
+        calls.append(tuple(hidden.shape))
+        out = hidden.float() @ emb.float().t()
+        if bias is not None:
+            out = out + bias.float()
+        return out.to(hidden.dtype)
+
+    monkeypatch.setattr(lg, "lm_head_logits", fake)
+    torch.manual_seed(0)
+    hidden = torch.randn(5, 64).to(torch.bfloat16)
+    emb = torch.randn(48, 64).to(torch.bfloat16)
+    bias = torch.randn(48).to(torch.bfloat16)
+    ref = ref_lp.LogitsProcessor(48, org_vocab_size=41)
+    ours = ref_lp.LogitsProcessor(48, org_vocab_size=41)
+    model = types.SimpleNamespace(logits_processor=ours,
+                                  lm_head=types.SimpleNamespace(weight=emb))
+    assert lg.install(model)
+    for b in (None, bias):
+        want = ref._get_logits(hidden, emb, b)
+        got = ours._get_logits(hidden, emb, b)
+        assert got.shape == want.shape == (5, 41)
+        assert torch.allclose(got.float(), want.float(), atol=0.13, rtol=2e-2)
+    assert calls == [(5, 64), (5, 64)]
+    # a rank the gather does not deliver to gets None, as in the reference
+    monkeypatch.setattr(vd, "tensor_model_parallel_gather", lambda x: None)
+    assert ours._get_logits(hidden, emb, None) is None
+    # models without an f16 / bf16 lm_head are left alone
+    assert not lg.install(types.SimpleNamespace(
+        logits_processor=ref_lp.LogitsProcessor(48),
+        lm_head=types.SimpleNamespace(weight=emb.float())))
+    assert not lg.install(types.SimpleNamespace())
+    # install_engine reports the seam
+    runner = types.SimpleNamespace(model=model)
+    engine = types.SimpleNamespace(
+        scheduler=None, model_config=None,
+        model_executor=types.SimpleNamespace(
+            driver_worker=types.SimpleNamespace(model_runner=runner, cache_engine=None)))
+    done = integration.install_engine(engine, scheduler=False, predictor=False, swap=False,
+                                      decode_inputs=False, sampler=False, prefill=False,
+                                      attention_backend=False)
+    assert done["logits"].startswith("LogitsProcessor._get_logits")

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kGemmThreads)
       const T* rrow = resid != nullptr ? resid + (int64_t)row * N + col : nullptr;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {          // 4 x 16-byte stores of 8 elements
+        if (col + v * 8 >= N) break;         // last column tile of an N that is not a multiple of BN
         alignas(16) T o[8];
         alignas(16) T rs[8];
         alignas(16) T bs[8];
@@ -291,7 +292,9 @@ __global__ void __launch_bounds__(kGemm2Threads, 1)
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_n = N / BN, num_m = (M + kBM - 1) / kBM, total = num_m * num_n;
+  // N need not be a multiple of BN (vocabulary shards of the lm_head): TMA zero-fills the W rows
+  // past N, the epilogue skips the columns past N
+  const int num_n = (N + BN - 1) / BN, num_m = (M + kBM - 1) / kBM, total = num_m * num_n;
   const int nk = (K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -375,11 +378,12 @@ __global__ void __launch_bounds__(kGemm2Threads, 1)
           for (int v = 0; v < 4; ++v) {
             alignas(16) T o[8];
             alignas(16) T bs[8];
-            if (bias != nullptr) *reinterpret_cast<uint4*>(bs) = __ldg(reinterpret_cast<const uint4*>(bias + col + v * 8));
+            const bool have_bias = bias != nullptr && col + v * 8 < N;
+            if (have_bias) *reinterpret_cast<uint4*>(bs) = __ldg(reinterpret_cast<const uint4*>(bias + col + v * 8));
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               float x = __uint_as_float(r[v * 8 + e]);
-              if (bias != nullptr) x += ST<T>::to_f(bs[e]);
+              if (have_bias) x += ST<T>::to_f(bs[e]);
               if (RELU) x = fmaxf(x, 0.f);
               o[e] = ST<T>::from_f(x);
             }
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(kGemm2Threads, 1)
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + (lane >> 3), ch = lane & 7;
           const int row = m0 + q * 32 + rr;
-          if (row < M) {
+          if (row < M && n0 + c * 64 + ch * 8 < N) {
             uint4 val = *reinterpret_cast<const uint4*>(slab_gen + rr * kSlabRow + ch * 16);
             const int64_t off = (int64_t)row * N + n0 + c * 64 + ch * 8;
             if (resid != nullptr) {
@@ -820,7 +824,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
                                      gemm_smem_bytes<BN>()));
       configured = true;
     }
-    dim3 grid(N / BN, (M + kBM - 1) / kBM);
+    dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM);
     launch(kern, grid, dim3(kGemmThreads), (size_t)gemm_smem_bytes<BN>(), stream, ma, mb, (T*)D,
            (const T*)bias, (const T*)resid, M, N, K);
     VLTR_LAUNCH_CHECK("opt_gemm");
@@ -833,7 +837,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
                                    gemm2_smem_bytes<BN>()));
     configured = true;
   }
-  const int total = (N / BN) * ((M + kBM - 1) / kBM);
+  const int total = ((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
   const int ctas = total < num_sms() ? total : num_sms();
   launch(kern, dim3(ctas), dim3(kGemm2Threads), (size_t)gemm2_smem_bytes<BN>(), stream, ma, mb,
          (T*)D, (const T*)bias, (const T*)resid, M, N, K);
@@ -845,13 +849,13 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
 static int gemm(const void* A, const void* W, void* D, const void* bias, const void* resid,
                 int M, int N, int K, int relu, int dtype, cudaStream_t stream) {
   VLTR_CHECK(M > 0 && N > 0 && K > 0, VLTR_ERR_INVALID, "opt_gemm: empty problem");
-  VLTR_CHECK(N % 64 == 0 && K % 8 == 0, VLTR_ERR_UNSUPPORTED,
-             "opt_gemm: N %d must be a multiple of 64 and K %d of 8", N, K);
+  VLTR_CHECK(N % 8 == 0 && K % 8 == 0, VLTR_ERR_UNSUPPORTED,
+             "opt_gemm: N %d and K %d must be multiples of 8", N, K);
   VLTR_CHECK(((uintptr_t)A | (uintptr_t)W | (uintptr_t)D | (uintptr_t)bias | (uintptr_t)resid) % 16 == 0,
              VLTR_ERR_INVALID, "opt_gemm: operands must be 16-byte aligned");
   // wide tiles when they still give every SM a CTA, else narrow ones
-  const int tiles128 = (N / 128) * ((M + kBM - 1) / kBM);
-  const bool wide = N % 128 == 0 && tiles128 >= num_sms();
+  const int tiles128 = ((N + 127) / 128) * ((M + kBM - 1) / kBM);
+  const bool wide = tiles128 >= num_sms();
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, kBM, dtype);
   if (rc) return rc;
@@ -1028,4 +1032,19 @@ extern "C" int vltr_opt_gemm(const void* A, const void* W, void* D, const void* 
                              const void* resid, int M, int N, int K, int relu, int dtype,
                              void* stream) {
   return vltr::opt::gemm(A, W, D, bias, resid, M, N, K, relu, dtype, (cudaStream_t)stream);
+}
+
+// logits = hidden . lm_head^T (+ bias): LogitsProcessor._get_logits
+// (vllm/model_executor/layers/logits_processor.py:61-64) on the same tcgen05 dense layer.  The
+// vocabulary shard of a tensor-parallel lm_head (32000 / 8 = 4000 rows) is not a multiple of the
+// tile width: the last column tile is partial.
+extern "C" int vltr_lm_head_logits(const void* hidden, const void* weight, const void* bias,
+                                   void* logits, int num_rows, int vocab_rows, int hidden_size,
+                                   int dtype, void* stream) {
+  using namespace vltr;
+  VLTR_CHECK(num_rows >= 0 && vocab_rows >= 0 && hidden_size > 0, VLTR_ERR_INVALID,
+             "lm_head_logits: negative size");
+  if (num_rows == 0 || vocab_rows == 0) return VLTR_OK;
+  return opt::gemm(hidden, weight, logits, bias, nullptr, num_rows, vocab_rows, hidden_size, 0,
+                   dtype, (cudaStream_t)stream);
 }

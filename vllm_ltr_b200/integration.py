@@ -6,7 +6,8 @@
     llm = LLM(...)                          # the unmodified reference engine
     from vllm_ltr_b200.integration import install_engine
     print(install_engine(llm.llm_engine))   # scheduler tick, predictor, swap path, decode inputs,
-                                            # sampler, attention backend, prefill kernel
+                                            # sampler, lm_head logits, attention backend,
+                                            # prefill kernel
 
 Each piece is optional and reported; pieces whose preconditions do not hold (schedule_type is not
 "opt*", no predictor configured, Ray workers instead of an in-process driver worker) are skipped
@@ -33,7 +34,7 @@ def _release_aux_engine(aux) -> None:
 
 def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap: bool = True,
                    decode_inputs: bool = True, sampler: bool = True, prefill: bool = True,
-                   attention_backend: bool = True,
+                   attention_backend: bool = True, logits: bool = True,
                    sampler_seed: Optional[int] = None,
                    release_reference_predictor: bool = True) -> Dict[str, str]:
     done: Dict[str, str] = {}
@@ -99,6 +100,18 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
                                    "other request goes to the engine's own Sampler)")
             else:
                 done["sampler"] = "skipped: model has no .sampler attribute"
+
+    if logits:
+        model = getattr(runner, "model", None)
+        if model is None:
+            done["logits"] = "skipped: no in-process model"
+        else:
+            from . import logits as lg
+            if lg.install(model):
+                done["logits"] = ("LogitsProcessor._get_logits: lm_head matmul on the tcgen05 "
+                                  "dense layer (vltr_lm_head_logits)")
+            else:
+                done["logits"] = "skipped: model has no f16 / bf16 lm_head + logits_processor"
 
     if attention_backend:
         model = getattr(runner, "model", None)

@@ -1,0 +1,57 @@
+#!/bin/bash
+# round-2 (second half) GPU session.  STAGES selects what runs; everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+stage() { echo "=== $1 ($(date +%T))" | tee -a $O/session3.log; }
+export_rep() {
+  local rep=$O/$1.ncu-rep
+  [ -f $rep ] || return 0
+  ncu -i $rep --page raw --csv > $O/$1.raw.csv 2>/dev/null
+  local sz=$(stat -c %s $rep)
+  if [ $sz -gt 14000000 ]; then rm -f $rep; fi
+}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt 2>&1
+for s in ${STAGES:-quick attn cache}; do
+case $s in
+quick) stage "targeted tests"
+  timeout 900 python -m pytest tests/test_gpu_cache.py tests/test_gpu_logits.py tests/test_gpu_golden.py -x -q -m gpu -p no:cacheprovider > $O/pytest_quick.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -6 $O/pytest_quick.log
+  timeout 900 python -m pytest tests/test_gpu_predictor.py -x -q -m gpu -k dense_layer -p no:cacheprovider > $O/pytest_dense.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -4 $O/pytest_dense.log;;
+attntests) stage "attention tests"
+  timeout 1500 python -m pytest tests/test_gpu_attention.py tests/test_gpu_hotpath.py tests/test_gpu_properties.py -x -q -m gpu -p no:cacheprovider > $O/pytest_attn.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -8 $O/pytest_attn.log;;
+attn) stage "attention timing"
+  timeout 600 python tools/attn_tune.py --ref --cases ${ATTN_CASES:-8b-gqa-fp8:256:trace,8b-gqa-fp8:256:2048,8b-gqa-bf16:256:trace,7b-mha-bf16:256:trace,70b-tp8-bf16:256:trace} --json $O/attn_tune.json > $O/attn_tune.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  cat $O/attn_tune.log;;
+cache) stage "reshape_and_cache bench"
+  timeout 600 python tools/cache_bench.py --json $O/cache_bench.json > $O/cache_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  cat $O/cache_bench.log;;
+ncu) stage "ncu: e5m2 attention, reshape_and_cache"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 4 -c 1 -f -o $O/attn_fp8_prof python tools/attn_tune.py --cases 8b-gqa-fp8:256:trace > $O/ncu_attn_fp8.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  export_rep attn_fp8_prof
+  timeout 600 ncu --set full --clock-control none -k regex:reshape_and_cache -s 40 -c 3 -f -o $O/cache_prof python tools/cache_bench.py --n 8 > $O/ncu_cache.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  export_rep cache_prof;;
+tests) stage "pytest -m gpu (full)"
+  timeout 2400 python -m pytest tests -x -q -m gpu -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -15 $O/pytest_gpu.log;;
+smoke) stage "smoke"
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "rc=$?" | tee -a $O/session3.log; tail -3 $O/smoke.log;;
+bench) stage "bench.py default"
+  timeout 1500 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "rc=$?" | tee -a $O/session3.log
+  head -c 7000 $O/bench_default.json; tail -5 $O/bench_default.err;;
+benchref) stage "bench.py --impl reference"
+  timeout 600 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err; echo "rc=$?" | tee -a $O/session3.log
+  head -c 1500 $O/bench_reference.json;;
+launches) stage "ncu launch list of bench.py"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --trace off --no-extras --no-cpu-baseline > $O/launches_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log;;
+enginetest) stage "engine test"
+  timeout 1800 python -m pytest tests/test_gpu_engine.py -x -q -m gpu -p no:cacheprovider > $O/pytest_engine.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -8 $O/pytest_engine.log;;
+profile) stage "engine profile b200"
+  timeout 900 python tools/engine_trace.py --arm b200 --model llama-2-7b --num-prompts 10000 --stop-after 1000 --max-steps 260 --profile 200:40:$O/engine_profile_b200.txt --json $O/e_prof_b200.json > $O/e_prof_b200.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  head -40 $O/engine_profile_b200.txt;;
+esac
+done
+stage done

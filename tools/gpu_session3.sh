@@ -25,6 +25,16 @@ attntests) stage "attention tests"
 attn) stage "attention timing"
   timeout 600 python tools/attn_tune.py --ref --cases ${ATTN_CASES:-8b-gqa-fp8:256:trace,8b-gqa-fp8:256:2048,8b-gqa-bf16:256:trace,7b-mha-bf16:256:trace,70b-tp8-bf16:256:trace} --json $O/attn_tune.json > $O/attn_tune.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   cat $O/attn_tune.log;;
+mb4) stage "e5m2 attention: 128-register build (4 CTAs/SM) vs default"
+  MB4=$PWD/vllm_ltr_b200/libvllm_ltr_b200_mb4.so
+  C=8b-gqa-fp8:256:trace,8b-gqa-fp8:256:2048,8b-gqa-fp8:64:trace
+  echo "--- default build" > $O/attn_mb4.log
+  timeout 300 python tools/attn_tune.py --grid fp8 --cases $C >> $O/attn_mb4.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  echo "--- VLTR_ATTN_FP8_MINB=4 build" >> $O/attn_mb4.log
+  VLTR_LIB=$MB4 timeout 300 python tools/attn_tune.py --grid fp8 --cases $C >> $O/attn_mb4.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  cat $O/attn_mb4.log
+  VLTR_LIB=$MB4 timeout 900 python -m pytest tests/test_gpu_attention.py -x -q -m gpu -k "fp8 or e5m2" -p no:cacheprovider > $O/pytest_attn_mb4.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -4 $O/pytest_attn_mb4.log;;
 cache) stage "reshape_and_cache bench"
   timeout 600 python tools/cache_bench.py --json $O/cache_bench.json > $O/cache_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   cat $O/cache_bench.log;;

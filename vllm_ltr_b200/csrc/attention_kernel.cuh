@@ -535,8 +535,20 @@ __device__ __forceinline__ void claim(Item& it, int pending_id, const Params& p,
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
+// Resident CTAs per SM the register allocation aims at (0 = the compiler's default, which lands
+// on 168 registers = three 4-warp CTAs for the tensor-core path).  The e5m2 tiles are half the
+// size, four CTAs fit in shared memory: VLTR_ATTN_FP8_MINB=4 caps those kernels at 128 registers
+// (a few spilled values per tile, L1-resident) for 16 instead of 12 resident warps.
+#ifndef VLTR_ATTN_FP8_MINB
+#define VLTR_ATTN_FP8_MINB 0
+#endif
+template <typename T, typename CT, int GT, bool MMA>
+constexpr int min_ctas_per_sm() {
+  return (MMA && GT == 8 && !std::is_same<T, CT>::value) ? VLTR_ATTN_FP8_MINB : 0;
+}
+
 template <typename T, typename CT, int D, int BS, int GT, bool MMA>
-__global__ void __launch_bounds__(128) paged_attention_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_attention_kernel(const __grid_constant__ Params p) {
   using C = Cfg<T, CT, D, BS, GT, MMA>;
   using QS = typename C::QS;
   using MT = typename C::MT;

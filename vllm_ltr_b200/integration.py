@@ -35,6 +35,7 @@ def _release_aux_engine(aux) -> None:
 def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap: bool = True,
                    decode_inputs: bool = True, sampler: bool = True, prefill: bool = True,
                    attention_backend: bool = True, logits: bool = True,
+                   step_broadcast: bool = True,
                    sampler_seed: Optional[int] = None,
                    release_reference_predictor: bool = True) -> Dict[str, str]:
     done: Dict[str, str] = {}
@@ -125,6 +126,15 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
                 done["attention_backend"] = f"skipped: {e}"
         else:
             done["attention_backend"] = "skipped: no in-process model"
+
+    if step_broadcast:
+        try:
+            from . import step_broadcast as sb
+            mods = sb.install()
+            done["step_broadcast"] = ("broadcast_tensor_dict: one coalesced buffer per call "
+                                      f"(bound in {len(mods)} modules; a bypass at world size 1)")
+        except ImportError as e:
+            done["step_broadcast"] = f"skipped: {e}"
 
     if prefill:
         try:

@@ -35,6 +35,11 @@ mb4) stage "e5m2 attention: 128-register build (4 CTAs/SM) vs default"
   cat $O/attn_mb4.log
   VLTR_LIB=$MB4 timeout 900 python -m pytest tests/test_gpu_attention.py -x -q -m gpu -k "fp8 or e5m2" -p no:cacheprovider > $O/pytest_attn_mb4.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   tail -4 $O/pytest_attn_mb4.log;;
+timeline) stage "attention per-warp timeline (trace build) + split grid"
+  C=${ATTN_CASES:-8b-gqa-fp8:256:trace,8b-gqa-bf16:256:trace}
+  VLTR_LIB=$PWD/vllm_ltr_b200/libvllm_ltr_b200_trace.so timeout 600 python tools/attn_tune.py --trace --cases $C > $O/attn_timeline.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  [ -n "${ATTN_GRID:-}" ] && timeout 600 python tools/attn_tune.py --grid $ATTN_GRID --cases $C >> $O/attn_timeline.log 2>&1
+  cat $O/attn_timeline.log;;
 cache) stage "reshape_and_cache bench"
   timeout 600 python tools/cache_bench.py --json $O/cache_bench.json > $O/cache_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   cat $O/cache_bench.log;;

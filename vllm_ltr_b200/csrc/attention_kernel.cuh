@@ -367,28 +367,66 @@ __device__ __forceinline__ float4 load_cg_4(const void* base, int64_t elem, bool
   }
 }
 
+// Merge of a sequence's partitions by one warp.  Every load here is an L2 round trip on the
+// critical path of the warp that finished the sequence's last partition (the partials were just
+// written by other SMs), so the loads are issued in as few dependent waves as possible: lane j
+// fetches (max, sum) of partition j for HB heads at once, the first JB partial outputs of those
+// heads are requested in the same wave (they do not depend on the weights), the weights are
+// formed with shuffles while everything is in flight.  Up to 32 partitions per wave of
+// statistics (the host caps a sequence at 16, the reference's v2 entry at max_ctx / 512).
 template <typename T, int D>
 __device__ __forceinline__ void merge_partials(const Params& p, int seq, int head0, int nheads,
                                                int np, int lane) {
   constexpr int HB = 4, JB = 4;
   constexpr int NV = (D + 127) / 128;   // 4-element vectors per lane
   for (int h0 = 0; h0 < nheads; h0 += HB) {
-    float mx[HB], inv[HB];
+    int64_t base[HB];
+    float mx[HB], inv[HB], wl[HB];      // wl: weight of partition `lane` (np <= 32)
 #pragma unroll
     for (int hh = 0; hh < HB; ++hh) {
       const int h = min(h0 + hh, nheads - 1);
-      const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
-      float m = -INFINITY;
-      for (int j = lane; j < np; j += 32) m = fmaxf(m, __ldcg(p.max_logits + base + j));
+      base[hh] = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
+    }
+    // wave 1: statistics of partitions lane, lane + 32, ... (one load pair per head when np <= 32)
+    float mj[HB], sj[HB];
+#pragma unroll
+    for (int hh = 0; hh < HB; ++hh) {
+      mj[hh] = lane < np ? __ldcg(p.max_logits + base[hh] + lane) : -INFINITY;
+      sj[hh] = lane < np ? __ldcg(p.exp_sums + base[hh] + lane) : 0.f;
+    }
+    // wave 1, continued: the first JB partial outputs of every head
+    float4 v[HB][JB][NV];
+    auto fetch = [&](int j0) {
+#pragma unroll
+      for (int hh = 0; hh < HB; ++hh)
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          const int j = min(j0 + jj, np - 1);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int d = 4 * lane + 128 * i;
+            v[hh][jj][i] = (D % 128 == 0 || d < D)
+                               ? load_cg_4<T>(p.tmp_out, (base[hh] + j) * D + d, p.tmp_is_f32 != 0)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+    };
+    fetch(0);
+#pragma unroll
+    for (int hh = 0; hh < HB; ++hh) {
+      float m = mj[hh];
+      for (int j = lane + 32; j < np; j += 32) m = fmaxf(m, __ldcg(p.max_logits + base[hh] + j));
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      float sum = 0.f;
-      for (int j = lane; j < np; j += 32)
-        sum += __ldcg(p.exp_sums + base + j) * expf(__ldcg(p.max_logits + base + j) - m);
+      float sum = sj[hh] * expf(mj[hh] - m);          // lane >= np: 0 * exp(-inf) = 0
+      wl[hh] = sum;
+      for (int j = lane + 32; j < np; j += 32)
+        sum += __ldcg(p.exp_sums + base[hh] + j) * expf(__ldcg(p.max_logits + base[hh] + j) - m);
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       mx[hh] = m;
       inv[hh] = __fdividef(1.0f, sum + 1e-6f);
+      wl[hh] *= inv[hh];
     }
     float4 a[HB][NV];
 #pragma unroll
@@ -396,27 +434,23 @@ __device__ __forceinline__ void merge_partials(const Params& p, int seq, int hea
 #pragma unroll
       for (int i = 0; i < NV; ++i) a[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j0 = 0; j0 < np; j0 += JB) {
+      if (j0 > 0) fetch(j0);
       float w[HB][JB];
-      float4 v[HB][JB][NV];
 #pragma unroll
-      for (int hh = 0; hh < HB; ++hh) {
-        const int h = min(h0 + hh, nheads - 1);
-        const int64_t base = ((int64_t)seq * p.num_heads + head0 + h) * p.n_part;
+      for (int hh = 0; hh < HB; ++hh)
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
-          const int j = min(j0 + jj, np - 1);
-          w[hh][jj] = j0 + jj < np ? __ldcg(p.exp_sums + base + j) *
-                                         expf(__ldcg(p.max_logits + base + j) - mx[hh]) * inv[hh]
-                                   : 0.f;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const int d = 4 * lane + 128 * i;
-            v[hh][jj][i] = (D % 128 == 0 || d < D)
-                               ? load_cg_4<T>(p.tmp_out, (base + j) * D + d, p.tmp_is_f32 != 0)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int j = j0 + jj;
+          float wj;
+          if (j0 + JB <= 32) {          // warp-uniform: the weights of this chunk sit in lanes
+            wj = __shfl_sync(0xffffffffu, wl[hh], j & 31);
+          } else {
+            const int jc = min(j, np - 1);
+            wj = __ldcg(p.exp_sums + base[hh] + jc) *
+                 expf(__ldcg(p.max_logits + base[hh] + jc) - mx[hh]) * inv[hh];
           }
+          w[hh][jj] = j < np ? wj : 0.f;
         }
-      }
 #pragma unroll
       for (int hh = 0; hh < HB; ++hh)
 #pragma unroll

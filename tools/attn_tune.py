@@ -121,6 +121,8 @@ def main():
                {"attn_min_tokens": 128}, {"attn_min_tokens": 256}],
         "ctas": [{}, {"attn_ctas": 2}, {"attn_ctas": 2, "attn_stages": 3},
                  {"attn_ctas": 2, "attn_stages": 4}, {"attn_ctas": 3, "attn_stages": 3}],
+        "cap": [{}, {"attn_cap_tokens": 384}, {"attn_cap_tokens": 256}, {"attn_cap_tokens": 128},
+                {"attn_ctas": 2, "attn_cap_tokens": 256}],
         "fp8": [{}, {"attn_stages": 3}, {"attn_stages": 4}, {"attn_ctas": 3}],
         # round 2: the two-launch (split) mode of the latency-bound regime
         "split": [{}, {"attn_split": -1}, {"attn_split": 1}, {"attn_split": 1, "attn_min_tokens": 32},

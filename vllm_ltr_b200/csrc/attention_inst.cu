@@ -23,15 +23,18 @@ static int launch_one(const Params& p0, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    // Resident warps per SM matter more than ring depth when the queue is long (measured,
-    // tools/attn_tune.py): three 4-warp CTAs with a 2-deep ring beat two with a 3-deep ring by
-    // 5-10% on 2-byte caches.  The e5m2 tiles are half the size: sized for four CTAs (2-deep
-    // ring) - registers admit three, and the shallow ring measured fastest for them.
-    const int ctas = want_ctas > 0 ? want_ctas : (C::FP8 ? 4 : 3);
+    // FMA path (one query head per kv head): resident warps matter more than ring depth when
+    // the queue is long (measured, tools/attn_tune.py): three 4-warp CTAs with a 2-deep ring
+    // beat two with a 3-deep ring by 2-5% on 2-byte caches.
+    // Round 2 (profiles/r02_attn_timeline.txt): the tensor-core path is bound by each warp's
+    // dependent chain, not by resident warps - with 2-byte caches two CTAs with a 3-deep ring
+    // beat three with a 2-deep one by 4-5 % (GQA trace batch 83 -> 79.5 us); the e5m2 variant
+    // (registers admit three CTAs) is best with three CTAs and a 3-deep ring.
+    const int ctas = want_ctas > 0 ? want_ctas : (MMA ? (C::FP8 ? 3 : 2) : (C::FP8 ? 4 : 3));
     int budget = sm_smem / ctas - 1024 - kPlanBytes;       // 1 KiB per CTA is reserved by the system
     if (budget > max_optin - kPlanBytes) budget = max_optin - kPlanBytes;
     int warps = want_warps > 0 ? want_warps : 4, stages = 0;
-    const int top = want_stages > 0 ? want_stages : 6;
+    const int top = want_stages > 0 ? want_stages : (MMA && C::FP8 ? 3 : 6);
     // first choice: the wanted CTAs/SM with as many warps as fit; last resort: one CTA per SM
     for (int pass = 0; pass < 2 && stages < 2; ++pass) {
       const int lim = pass == 0 ? budget : max_optin - kPlanBytes;

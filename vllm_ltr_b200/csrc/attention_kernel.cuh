@@ -780,17 +780,21 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
   // take, early enough that its tiles are landing while the current item finishes.
   // Everything above reads only step inputs (context lengths) and builds shared-memory state:
   // with programmatic dependent launch it ran while the previous kernel (reshape_and_cache, which
-  // writes the newest token's K/V) was still draining.  From here on the queue counters, the
-  // query and the KV cache are read.
-  pdl_wait();
-  pdl_trigger();
-  if (tr != nullptr && lane == 0) tr[1] = gtime();
-  if (p.plan_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.plan_out[0] = part_blocks;
+  // writes the newest token's K/V) was still draining.  After the wait the query and the KV cache
+  // are read.
+  // The first work item is claimed here too, still ahead of the wait: the queue counter of this
+  // launch was zeroed by the launch that used the slot kCounterSlots launches ago, and an item is
+  // made of step inputs only (context length, block ids) - two L2 round trips that would
+  // otherwise sit between the end of the previous kernel and the first KV request.
   Item cur, nxt;
   nxt.valid = 0;
   int pend = fetch_id(p, lane);
   bool pend_valid = false, nxt_ready = false;
   claim(cur, pend, p, plan, total_items, part_blocks, BS, lane);
+  pdl_wait();
+  pdl_trigger();
+  if (tr != nullptr && lane == 0) tr[1] = gtime();
+  if (p.plan_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.plan_out[0] = part_blocks;
   pump(cur);
   auto advance = [&]() {
     if (!nxt_ready) {

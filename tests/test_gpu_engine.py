@@ -54,7 +54,7 @@ def arms(tmp_path_factory):
 def test_engine_runs_the_plugin(arms):
     _, b = arms
     inst = b["engine"]["installed"]
-    for k in ("scheduler", "predictor", "swap", "decode_inputs", "sampler", "prefill",
+    for k in ("scheduler", "predictor", "swap", "decode_inputs", "sampler", "logits", "prefill",
               "attention_backend"):
         assert not inst[k].startswith("skipped"), (k, inst[k])
     s = b["summary"]

@@ -40,6 +40,18 @@ timeline) stage "attention per-warp timeline (trace build) + split grid"
   VLTR_LIB=$PWD/vllm_ltr_b200/libvllm_ltr_b200_trace.so timeout 600 python tools/attn_tune.py --trace --cases $C > $O/attn_timeline.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   [ -n "${ATTN_GRID:-}" ] && timeout 600 python tools/attn_tune.py --grid $ATTN_GRID --cases $C >> $O/attn_timeline.log 2>&1
   cat $O/attn_timeline.log;;
+pair) stage "two KV blocks per iteration: default build (e5m2 only) vs PAIR=2 build (2-byte caches too)"
+  P2=$PWD/vllm_ltr_b200/libvllm_ltr_b200_p2.so
+  C=8b-gqa-fp8:256:trace,8b-gqa-fp8:256:2048,8b-gqa-bf16:256:trace,70b-tp8-bf16:256:trace,8b-gqa-fp8:64:trace,8b-gqa-bf16:64:trace
+  echo "--- default build (VLTR_ATTN_PAIR=1)" > $O/attn_pair.log
+  timeout 300 python tools/attn_tune.py --cases $C >> $O/attn_pair.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  echo "--- VLTR_ATTN_PAIR=2 build" >> $O/attn_pair.log
+  VLTR_LIB=$P2 timeout 300 python tools/attn_tune.py --grid ctas --cases $C >> $O/attn_pair.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  cat $O/attn_pair.log
+  timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_hotpath.py tests/test_gpu_properties.py -x -q -m gpu -p no:cacheprovider > $O/pytest_attn.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -4 $O/pytest_attn.log
+  VLTR_LIB=$P2 timeout 900 python -m pytest tests/test_gpu_attention.py -x -q -m gpu -p no:cacheprovider > $O/pytest_attn_p2.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -4 $O/pytest_attn_p2.log;;
 cache) stage "reshape_and_cache bench"
   timeout 600 python tools/cache_bench.py --json $O/cache_bench.json > $O/cache_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   cat $O/cache_bench.log;;

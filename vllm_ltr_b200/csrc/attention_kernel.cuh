@@ -84,6 +84,13 @@ struct Params {
 #ifndef VLTR_ATTN_TRACE
 #define VLTR_ATTN_TRACE 0
 #endif
+// KV blocks per loop iteration of the tensor-core path: 0 = one, 1 = two for e5m2 caches,
+// 2 = two for 2-byte caches as well.  Measured (profiles/r02_attn_pair.txt): two blocks per
+// iteration change nothing (e5m2 trace batch 47.5 vs 46.3 us, bf16 GQA 77.7 vs 76.1 us) - the
+// tile loop is not what bounds these launches - so the default stays one.
+#ifndef VLTR_ATTN_PAIR
+#define VLTR_ATTN_PAIR 0
+#endif
 // two interleaved accumulator chains for S^T = K.Q^T (tensor-core path)
 #ifndef VLTR_ATTN_SPLIT_QK
 #define VLTR_ATTN_SPLIT_QK 1
@@ -904,7 +911,18 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
       tr_loop0 = clock64();
       if (lane == 0) tr[8] = gtime();       // item set up (claimed, q staged)
     }
-    for (int tile = 0; tile < ntiles; ++tile) {
+    // Tensor-core path, e5m2 cache: TWO KV blocks per loop iteration when the item has them.
+    // One warp's tile is a dependent chain (shared loads -> byte permutes -> mma chain -> shuffle
+    // max -> exp -> transpose -> mma) of ~1800 cycles whatever its instruction count
+    // (profiles/r02_attn_timeline.txt); two blocks give the warp two independent chains to
+    // interleave and one softmax update (shuffles, rescale test) per 32 tokens.  NTP is the
+    // compile-time capacity, `nt` (warp-uniform) what this iteration really has; the second
+    // block's code is skipped (QK, PV) or masked (softmax rows) when nt == 1.
+    constexpr int NTP =
+        (MMA && MTL == 1 && BS >= 16 && VLTR_ATTN_PAIR >= (C::FP8 ? 1 : 2)) ? 2 : 1;
+    constexpr int MT2 = NTP * MTL;
+    for (int tile = 0; tile < ntiles;) {
+      const int nt = (NTP == 2 && ntiles - tile >= 2) ? 2 : 1;
       if (!pend_valid && !nxt_ready && ntiles - tile <= S + 2) {
         pend = fetch_id(p, lane);
         pend_valid = true;
@@ -914,25 +932,35 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
         pend_valid = false;
         pump(nxt);
       }
+      // ring stages of the iteration's blocks (consecutive, wrapping)
+      const int stage_1 = stage_c + 1 == S ? 0 : stage_c + 1;
+      const uint32_t phase_1 = stage_c + 1 == S ? phase_c ^ 1u : phase_c;
       const uint32_t ktile = tiles_s + stage_c * 2 * C::TILE_BYTES;
       const uint32_t vtile = ktile + C::TILE_BYTES;
+      const uint32_t ktile1 = tiles_s + stage_1 * 2 * C::TILE_BYTES;   // used when NTP == 2
+      const uint32_t kt[2] = {ktile, ktile1};
+      const uint32_t vt_[2] = {vtile, ktile1 + (uint32_t)C::TILE_BYTES};
       long long tw0 = 0;
       if (tr != nullptr) tw0 = clock64();
       mbar_wait(bars + 8 * stage_c, phase_c);
+      if (NTP == 2 && nt == 2) mbar_wait(bars + 8 * stage_1, phase_1);
       if (tr != nullptr) {
         tr_wait += clock64() - tw0;
         if (tr_tiles == 0 && lane == 0) tr[2] = gtime();
-        ++tr_tiles;
+        tr_tiles += nt;
       }
       const int tok0 = (blk0 + tile) * BS;
-      const bool last_partial = (blk0 + tile == nblk_ctx - 1) && (ctx % BS != 0);
+      // only the context's last block can be partial; it is the iteration's last block
+      const int last_u = nt - 1;
+      const bool last_partial = (blk0 + tile + last_u == nblk_ctx - 1) && (ctx % BS != 0);
 
       if constexpr (MMA) {
         // ---- tensor-core path -------------------------------------------------------------------
         if (last_partial) {
           // zero the out-of-context columns of the V tile (they may hold NaNs, p = 0 there)
-          const int valid = ctx - tok0;
-          unsigned char* vt = wbase + (size_t)stage_c * 2 * C::TILE_BYTES + C::TILE_BYTES;
+          const int valid = ctx - (tok0 + last_u * BS);
+          const int stage_l = last_u == 0 ? stage_c : stage_1;
+          unsigned char* vt = wbase + (size_t)stage_l * 2 * C::TILE_BYTES + C::TILE_BYTES;
           for (int i = lane; i < D * BS; i += 32)
             if (i % BS >= valid) reinterpret_cast<CT*>(vt)[i] = CT(0);
           // these generic-proxy writes must be ordered before the TMA refill of this stage
@@ -940,15 +968,18 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
           __syncwarp();
         }
         const int j = lane >> 3;      // ldmatrix: lane supplies row (lane & 7) of matrix j
-        float st[MTL][NH][4];         // S^T: (token g | g+8 of M tile mt, heads 2t4,2t4+1 of tile nh)
+        // S^T: (token g | g+8 of M tile mt, heads 2t4,2t4+1 of tile nh); M tile mt belongs to
+        // block u = mt / MTL of the iteration
+        float st[MT2][NH][4];
 #pragma unroll
-        for (int mt = 0; mt < MTL; ++mt)
+        for (int mt = 0; mt < MT2; ++mt)
 #pragma unroll
           for (int nh = 0; nh < NH; ++nh) st[mt][nh][0] = st[mt][nh][1] = st[mt][nh][2] = st[mt][nh][3] = 0.f;
         // the KS products of a tile accumulate into the same registers: a dependent chain of KS
         // tensor-core latencies per warp.  SPLIT_QK keeps a second accumulator for the odd
-        // k-steps (two chains of KS / 2) and adds them at the end.
-        constexpr bool SPLIT_QK = VLTR_ATTN_SPLIT_QK && C::KS >= 4 && C::KS % 2 == 0;
+        // k-steps (two chains of KS / 2) and adds them at the end (not needed with two blocks
+        // per iteration: they are two chains already).
+        constexpr bool SPLIT_QK = VLTR_ATTN_SPLIT_QK && NTP == 1 && C::KS >= 4 && C::KS % 2 == 0;
         float st2[SPLIT_QK ? MTL : 1][SPLIT_QK ? NH : 1][4];
         if constexpr (SPLIT_QK) {
 #pragma unroll
@@ -960,16 +991,19 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
 #pragma unroll
         for (int ks = 0; ks < C::KS; ++ks) {
 #pragma unroll
-          for (int mt = 0; mt < MTL; ++mt) {
+          for (int mt = 0; mt < MT2; ++mt) {
+            const int u = mt / MTL, ms = mt % MTL;      // block of the iteration, M tile inside it
+            if (NTP == 2 && u >= nt) continue;          // warp-uniform
+            const uint32_t kbase_ = kt[u];
             uint32_t a[4];
             if constexpr (!C::FP8) {
               // K tile [D/8][BS][8]: (chunk c, tokens 8b..8b+7) is one 8x8 b16 matrix, rows 16 B
               // apart.  A fragment: a0 = (tokens 0-7, k 0-7), a1 = (tokens 8-15, k 0-7),
               // a2 = (tokens 0-7, k 8-15), a3 = (tokens 8-15, k 8-15)
               if constexpr (BS >= 16) {
-                ldsm_x4(ktile + (((2 * ks + (j >> 1)) * BS + 16 * mt + 8 * (j & 1) + (lane & 7)) << 4), a);
+                ldsm_x4(kbase_ + (((2 * ks + (j >> 1)) * BS + 16 * ms + 8 * (j & 1) + (lane & 7)) << 4), a);
               } else {   // BS == 8: tokens 8..15 of the M tile do not exist
-                ldsm_x4(ktile + (((2 * ks + (j >> 1)) * BS + (lane & 7)) << 4), a);
+                ldsm_x4(kbase_ + (((2 * ks + (j >> 1)) * BS + (lane & 7)) << 4), a);
                 a[1] = 0u;
                 a[3] = 0u;
               }
@@ -978,11 +1012,11 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
               // thread's four k slots.  Which token sits in which row of the M tile is free
               // (the softmax runs down the rows, P^T inherits the order): rows g and g + 8 take
               // tokens prow0 and prow0 + 2 (see PERM above) so that V needs one load per row.
-              const uint32_t w0 = lds4(ktile + ((ks * BS + 16 * mt + prow0) << 4) + 4 * t4);
+              const uint32_t w0 = lds4(kbase_ + ((ks * BS + 16 * ms + prow0) << 4) + 4 * t4);
               a[0] = __byte_perm(w0, 0, 0x1404);
               a[2] = __byte_perm(w0, 0, 0x3424);
               if constexpr (BS >= 16) {
-                const uint32_t w1 = lds4(ktile + ((ks * BS + 16 * mt + prow0 + prow8) << 4) + 4 * t4);
+                const uint32_t w1 = lds4(kbase_ + ((ks * BS + 16 * ms + prow0 + prow8) << 4) + 4 * t4);
                 a[1] = __byte_perm(w1, 0, 0x1404);
                 a[3] = __byte_perm(w1, 0, 0x3424);
               } else {
@@ -993,7 +1027,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
 #pragma unroll
             for (int nh = 0; nh < NH; ++nh) {
               if (SPLIT_QK && (ks & 1))
-                mma16816<MT>(st2[mt][nh], a, qa[ks][nh], qa[ks][2 + nh]);
+                mma16816<MT>(st2[SPLIT_QK ? mt : 0][SPLIT_QK ? nh : 0], a, qa[ks][nh], qa[ks][2 + nh]);
               else
                 mma16816<MT>(st[mt][nh], a, qa[ks][nh], qa[ks][2 + nh]);
             }
@@ -1010,8 +1044,8 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
         // ---- online softmax down the token rows of each head column (log2 domain) --------------
         // only the context's last block can hold out-of-context tokens, and ALiBi is rare: the
         // common tile takes the short form (bit-identical: slope == 0 adds +0)
-        const bool plain = !last_partial && p.alibi_slopes == nullptr && BS >= 16;
-        uint32_t pb[MTL][NH][2];      // P^T as B operand: [0] tokens 2t4,2t4+1; [1] tokens 8+2t4,9+2t4
+        const bool plain = !last_partial && p.alibi_slopes == nullptr && BS >= 16 && nt == NTP;
+        uint32_t pb[MT2][NH][2];      // P^T as B operand: [0] tokens 2t4,2t4+1; [1] tokens 8+2t4,9+2t4
 #pragma unroll
         for (int nh = 0; nh < NH; ++nh) {
           float m_new[2];
@@ -1020,15 +1054,16 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
             const int c = 2 * nh + e;
             float mx = -INFINITY;
 #pragma unroll
-            for (int mt = 0; mt < MTL; ++mt) {
+            for (int mt = 0; mt < MT2; ++mt) {
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 float sv = st[mt][nh][2 * hh + e] * scale_l2;
                 if (!plain) {
-                  const int row = 16 * mt + prow8 * hh + prow0;
-                  const int tok = tok0 + row;
+                  const int u = mt / MTL;
+                  const int row = 16 * (mt % MTL) + prow8 * hh + prow0;
+                  const int tok = tok0 + u * BS + row;
                   sv += slope[c] * (float)(tok - ctx + 1);
-                  sv = (tok < ctx && row < BS) ? sv : -INFINITY;
+                  sv = (u < nt && tok < ctx && row < BS) ? sv : -INFINITY;
                 }
                 st[mt][nh][2 * hh + e] = sv;
                 mx = fmaxf(mx, sv);
@@ -1052,7 +1087,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
             }
           }
 #pragma unroll
-          for (int mt = 0; mt < MTL; ++mt) {
+          for (int mt = 0; mt < MT2; ++mt) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               if (BS >= 16 || hh == 0) {
@@ -1075,17 +1110,20 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
         }
         // ---- O^T += V^T . P^T -------------------------------------------------------------------
 #pragma unroll
-        for (int mt = 0; mt < MTL; ++mt) {
+        for (int dt = 0; dt < DT; ++dt) {
 #pragma unroll
-          for (int dt = 0; dt < DT; ++dt) {
+          for (int mt = 0; mt < MT2; ++mt) {
+            const int u = mt / MTL, ms = mt % MTL;
+            if (NTP == 2 && u >= nt) continue;          // warp-uniform: stale stage, p = 0
+            const uint32_t vbase_ = vt_[u];
             uint32_t a[4];
             if constexpr (!C::FP8) {
               // V tile [D][BS]: (rows 8b..8b+7, tokens 8c..8c+7) is one 8x8 matrix, rows 2*BS B
               // apart.  a0 = (d 0-7, tok 0-7), a1 = (d 8-15, tok 0-7), a2 = (d 0-7, tok 8-15), a3
               if constexpr (BS >= 16) {
-                ldsm_x4(vtile + ((16 * dt + 8 * (j & 1) + (lane & 7)) * BS + 16 * mt + 8 * (j >> 1)) * 2, a);
+                ldsm_x4(vbase_ + ((16 * dt + 8 * (j & 1) + (lane & 7)) * BS + 16 * ms + 8 * (j >> 1)) * 2, a);
               } else {
-                ldsm_x4(vtile + ((16 * dt + 8 * (j & 1) + (lane & 7)) * BS) * 2, a);
+                ldsm_x4(vbase_ + ((16 * dt + 8 * (j & 1) + (lane & 7)) * BS) * 2, a);
                 a[2] = 0u;
                 a[3] = 0u;
               }
@@ -1094,7 +1132,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
                 // e5m2 V tile [D][BS] bytes.  With the token rows of S^T permuted, the P^T
                 // fragments carry tokens 4t4, 4t4+1 (k slots 2t4, 2t4+1) and 4t4+2, 4t4+3 (k slots
                 // 2t4+8, 2t4+9): the four V bytes of a row are ONE 32-bit load
-                const uint32_t row0 = vtile + (16 * dt + g) * BS + 16 * mt + 4 * t4;
+                const uint32_t row0 = vbase_ + (16 * dt + g) * BS + 16 * ms + 4 * t4;
                 const uint32_t w0 = lds4(row0), w1 = lds4(row0 + 8 * BS);
                 a[0] = __byte_perm(w0, 0, 0x1404);
                 a[1] = __byte_perm(w1, 0, 0x1404);
@@ -1102,7 +1140,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
                 a[3] = __byte_perm(w1, 0, 0x3424);
               } else {
                 // block size 8: two 16-bit loads (tokens 2t4, 2t4+1 of rows g, g + 8)
-                const uint32_t row0 = vtile + (16 * dt + g) * BS + 16 * mt + 2 * t4;
+                const uint32_t row0 = vbase_ + (16 * dt + g) * BS + 16 * ms + 2 * t4;
                 uint32_t w0, w1;
                 asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w0) : "r"(row0));
                 asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w1) : "r"(row0 + 8 * BS));
@@ -1196,13 +1234,16 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
           }
         }
       }
-      __syncwarp();  // every lane is done with this stage (and with p_s)
-      --inflight;
-      if (++stage_c == S) {
-        stage_c = 0;
-        phase_c ^= 1;
+      __syncwarp();  // every lane is done with this iteration's stages (and with p_s)
+      for (int u = 0; u < nt; ++u) {
+        --inflight;
+        if (++stage_c == S) {
+          stage_c = 0;
+          phase_c ^= 1;
+        }
       }
-      // refill the freed stage: this item first, then the next one (lookahead across items)
+      tile += nt;
+      // refill the freed stages: this item first, then the next one (lookahead across items)
       pump(cur);
       if (nxt_ready) pump(nxt);
     }

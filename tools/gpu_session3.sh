@@ -77,7 +77,35 @@ benchref) stage "bench.py --impl reference"
   timeout 600 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err; echo "rc=$?" | tee -a $O/session3.log
   head -c 1500 $O/bench_reference.json;;
 launches) stage "ncu launch list of bench.py"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --trace off --no-extras --no-cpu-baseline > $O/launches_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log;;
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"paged_attention|merge_partials|reshape_and_cache|rms_|rope_|act_|rank_|gemm_tn|layernorm_kernel|embed_kernel|score_kernel|attention_kernel" -c 4000 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --launch eager --trace off --no-extras --no-cpu-baseline > $O/launches_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log;;
+fixed) stage "attention fixed cost (one tile per item)"
+  timeout 300 python tools/attn_tune.py --cases 8b-gqa-bf16:256:16,7b-mha-bf16:256:16,8b-gqa-fp8:256:16,70b-tp8-bf16:256:16,8b-gqa-bf16:256:128 > $O/attn_fixed.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  cat $O/attn_fixed.log;;
+gemmtests) stage "dense layer / logits / predictor tests"
+  timeout 900 python -m pytest tests/test_gpu_predictor.py tests/test_gpu_logits.py -x -q -m gpu -p no:cacheprovider > $O/pytest_gemm.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -4 $O/pytest_gemm.log
+  timeout 300 python - > $O/lm_head_time.log 2>&1 <<'PY'
+import torch, sys
+sys.path.insert(0, ".")
+from vllm_ltr_b200.logits import lm_head_logits
+dev = "cuda:0"
+for rows, vocab, hidden, dt in ((256, 32000, 4096, torch.float16), (256, 128256, 4096, torch.bfloat16), (64, 32000, 4096, torch.float16), (256, 4000, 8192, torch.bfloat16)):
+    h = torch.randn(rows, hidden, device=dev).to(dt)
+    ws = [(torch.randn(vocab, hidden, device=dev) * 0.02).to(dt) for _ in range(3)]   # rotate: > L2
+    def run(fn, n=30):
+        for w in ws: fn(h, w)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n): fn(h, ws[i % 3])
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+    ours = run(lambda a, w: lm_head_logits(a, w))
+    cub = run(lambda a, w: torch.matmul(a, w.t()))
+    gb = vocab * hidden * 2 / 1e3
+    print(f"lm_head rows={rows} vocab={vocab} hidden={hidden} {dt}: ours {ours:7.1f} us ({gb/ours:6.0f} GB/s of weights)  cuBLAS {cub:7.1f} us")
+PY
+  cat $O/lm_head_time.log;;
 enginetest) stage "engine test"
   timeout 1800 python -m pytest tests/test_gpu_engine.py -x -q -m gpu -p no:cacheprovider > $O/pytest_engine.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   tail -8 $O/pytest_engine.log;;

@@ -45,7 +45,12 @@ def launches(src, dst):
         a = agg.setdefault(name, [0, 0.0, d["Grid Size"], d["Block Size"]])
         a[0] += 1
         a[1] += v
-    ours = {k: v for k, v in agg.items() if "vltr" in k or "attn::" in k}
+    # ncu prints the bare function name for some builds (no namespace): match our kernels by name
+    mine = ("vltr", "attn::", "paged_attention", "merge_partials", "reshape_and_cache", "rms_",
+            "rope_", "act_", "rank_", "gemm_tn", "layernorm_kernel", "embed_kernel", "score_kernel",
+            "sample_kernel", "block_copy", "prefill_attention", "tp_fused", "fp8_kernel",
+            "add_pos_kernel", "attention_kernel")
+    ours = {k: v for k, v in agg.items() if any(m in k for m in mine)}
     tot = sum(v[1] for v in ours.values())
     with open(dst, "w") as f:
         f.write(f"# launch list ({src}): `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")

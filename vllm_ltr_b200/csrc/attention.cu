@@ -46,7 +46,7 @@ struct DevState {
 };
 static DevState g_dev[64];
 static std::mutex g_mu;
-constexpr size_t kTicketFloor = 65536;   // 256 sequences x 16 kv heads x 16 passes
+constexpr size_t kTicketFloor = 131072;  // 256 sequences x 32 kv heads x 16 passes
 constexpr size_t kWsFloor = (size_t)256 * 32 * 17 * (128 + 2) * sizeof(float);
 
 static int get_state(DevState** out) {
@@ -94,11 +94,16 @@ static int ensure_ws(DevState* st, int slot, size_t bytes, cudaStream_t stream) 
              "being captured; run one eager call of this shape before capturing", bytes);
   // beyond the pre-allocated floor (larger batches / more heads than the engine's limits): the
   // old buffer is retired alive, never freed
+  // Every slot grows now (launches rotate over the slots: a graph captured after ONE eager call
+  // of this shape must not meet a slot that still has to grow).
   const size_t want = bytes + bytes / 2;
-  char* fresh = nullptr;
-  VLTR_CUDA(cudaMalloc(&fresh, want));
-  st->ws[slot] = fresh;
-  st->ws_bytes[slot] = want;
+  for (int s = 0; s < kTicketSlots; ++s) {
+    if (st->ws_bytes[s] >= bytes) continue;
+    char* fresh = nullptr;
+    VLTR_CUDA(cudaMalloc(&fresh, want));
+    st->ws[s] = fresh;
+    st->ws_bytes[s] = want;
+  }
   return VLTR_OK;
 }
 static int ensure_tickets(DevState* st, int slot, size_t n, cudaStream_t stream) {
@@ -110,14 +115,17 @@ static int ensure_tickets(DevState* st, int slot, size_t n, cudaStream_t stream)
              "paged_attention: the ticket table must grow (%zu entries) while the stream is being "
              "captured; run one eager call of this shape before capturing", n);
   const size_t want = n + n / 2;
-  int* fresh = nullptr;
-  VLTR_CUDA(cudaMalloc(&fresh, sizeof(int) * want));
-  // plain (legacy-stream) memset: ordered before any later launch on a blocking stream, and
-  // followed by a synchronise for non-blocking ones - growth is a first-calls-only event
-  VLTR_CUDA(cudaMemset(fresh, 0, sizeof(int) * want));
+  for (int s = 0; s < kTicketSlots; ++s) {     // every slot, for the same reason as ensure_ws
+    if (st->ticket_cap[s] >= n) continue;
+    int* fresh = nullptr;
+    VLTR_CUDA(cudaMalloc(&fresh, sizeof(int) * want));
+    // plain (legacy-stream) memset: ordered before any later launch on a blocking stream, and
+    // followed by a synchronise for non-blocking ones - growth is a first-calls-only event
+    VLTR_CUDA(cudaMemset(fresh, 0, sizeof(int) * want));
+    st->tickets[s] = fresh;        // the previous table stays allocated (replayed graphs use it)
+    st->ticket_cap[s] = want;
+  }
   VLTR_CUDA(cudaDeviceSynchronize());
-  st->tickets[slot] = fresh;       // the previous table stays allocated (replayed graphs use it)
-  st->ticket_cap[slot] = want;
   return VLTR_OK;
 }
 

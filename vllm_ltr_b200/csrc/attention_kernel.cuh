@@ -45,7 +45,7 @@ namespace attn {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kMaxPlanSeqs = 1024;   // per-CTA partition plan lives in shared memory up to here
-constexpr int kPlanBytes = 8192;     // cum[n+1] ints + 2 x 66 ints (tail histogram) + n uint16
+constexpr int kPlanBytes = 8192;     // cum[n+1] ints + 4 x 66 + 8 ints (tail histograms) + n uint16
 
 struct Params {
   void* out;                    // [num_seqs, num_heads, D]  T
@@ -503,9 +503,11 @@ struct Item {
 // cum[s] = number of partitions of sequences < s (plan mode), in shared memory
 // The queue ticket is fetched one item AHEAD (lane 0 keeps the pending id in a register and only
 // broadcasts it here), so the atomic's round trip to L2 overlaps the previous item's work.
-__device__ __forceinline__ int fetch_id(const Params& p, int lane) {
+// The FIRST item of every warp is its own index (no atomic: one L2 round trip less in front of
+// the first KV request); the queue counter hands out the items after those.
+__device__ __forceinline__ int fetch_id(const Params& p, int lane, int first_dynamic) {
   int id = 0;
-  if (lane == 0) id = atomicAdd(&p.counters[0], 1);
+  if (lane == 0) id = atomicAdd(&p.counters[0], 1) + first_dynamic;
   return id;
 }
 // Order of the partial last partitions ("tails") in the queue, after all full partitions: bucket
@@ -617,8 +619,8 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
                                  ((C::P_BYTES + 15) / 16) * 16);   // S mbarriers
   const uint32_t q_sa = smem_u32(q_s), p_sa = smem_u32(p_s);
   int* cum = reinterpret_cast<int*>(smem_raw + (size_t)nwarps * wbytes);   // [kMaxPlanSeqs + 1]
-  int* hist = cum + kMaxPlanSeqs + 1;                                       // [132]
-  unsigned short* tail_order = reinterpret_cast<unsigned short*>(hist + 132);   // [kMaxPlanSeqs]
+  int* hist = cum + kMaxPlanSeqs + 1;                                       // [4 x 66 + 8]
+  unsigned short* tail_order = reinterpret_cast<unsigned short*>(hist + 272);   // [kMaxPlanSeqs]
   Plan plan{cum, tail_order, 0};
 
   if (lane == 0) {
@@ -665,68 +667,105 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
     }
     // partition plan (every CTA builds its own copy; num_seqs <= 1024): prefix sums of the FULL
     // partitions per sequence, and the sequences with a partial last partition counting-sorted
-    // by its length, longest first.  All threads fetch the context lengths at once (one L2
-    // round trip); everything else runs out of shared memory.
-    for (int i = threadIdx.x; i < 132; i += blockDim.x) hist[i] = 0;
+    // by its length, longest first, sequence order inside a bucket (every CTA must build the SAME
+    // order).  This runs in every CTA of every launch, in front of the first KV request, so it is
+    // kept to one L2 round trip (the context lengths) and three barriers: each warp takes a
+    // contiguous range of sequences, counts its buckets in its own histogram row with
+    // match_any, warp 0 turns the rows into start offsets (bucket descending, then warp) and
+    // scans the full-partition counts, then every warp scatters its own sequences.
+    constexpr int NB = 66;                                     // buckets 0..65 (tail_bucket)
+    for (int i = threadIdx.x; i < 4 * NB + 8; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int s = threadIdx.x; s < p.num_seqs; s += blockDim.x) {
-      const int c = p.context_lens[s];
-      cum[s + 1] = c / part_tokens;
-      const int rem = c % part_tokens;
-      if (rem != 0 || c == 0)           // empty context: a zero-tile tail item writes zeros
-        atomicAdd(&hist[tail_bucket(c, rem, part_tokens, BS)], 1);
+    const int nchunks = (p.num_seqs + 31) >> 5;
+    const int per_warp = (nchunks + nwarps - 1) / nwarps;      // chunks of 32 sequences per warp
+    const int chunk0 = warp * per_warp, chunk1 = min(chunk0 + per_warp, nchunks);
+    int* my_hist = hist + (warp & 3) * NB;
+    for (int ch = chunk0; ch < chunk1; ++ch) {
+      const int s = ch * 32 + lane;
+      int bkt = -1;
+      if (s < p.num_seqs) {
+        const int c = p.context_lens[s];
+        cum[s + 1] = c / part_tokens;
+        const int rem = c % part_tokens;
+        if (rem != 0 || c == 0)         // empty context: a zero-tile tail item writes zeros
+          bkt = tail_bucket(c, rem, part_tokens, BS);
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, bkt);
+      if (bkt >= 0 && lane == __ffs(same) - 1) my_hist[bkt] += __popc(same);
+      __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {
+      // start offsets: position q = 65 - bucket ascending; lane owns q = 3*lane .. 3*lane + 2
+      int tot[3], before[3][4];
+      int mine = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int q = 3 * lane + k;
+        tot[k] = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          before[k][w] = tot[k];
+          if (q < NB) tot[k] += hist[w * NB + (NB - 1 - q)];
+        }
+        mine += tot[k];
+      }
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int start = incl - mine;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int q = 3 * lane + k;
+        if (q < NB) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) hist[w * NB + (NB - 1 - q)] = start + before[k][w];
+        }
+        start += tot[k];
+      }
+      if (lane == 31) hist[4 * NB] = incl;                     // number of tail items
+      // inclusive scan of the full-partition counts
       int carry = 0;
       for (int base = 0; base < p.num_seqs; base += 32) {
         const int s = base + lane;
         const int n = s < p.num_seqs ? cum[s + 1] : 0;
-        int incl = n;
+        int inc2 = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
+          const int v = __shfl_up_sync(0xffffffffu, inc2, o);
+          if (lane >= o) inc2 += v;
         }
         __syncwarp();
-        if (s < p.num_seqs) cum[s + 1] = carry + incl;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (s < p.num_seqs) cum[s + 1] = carry + inc2;
+        carry += __shfl_sync(0xffffffffu, inc2, 31);
       }
-      if (lane == 0) {
-        cum[0] = 0;
-        int run = 0;                    // descending bucket offsets
-        for (int b = 65; b >= 0; --b) {
-          hist[66 + b] = run;
-          run += hist[b];
-        }
-      }
+      if (lane == 0) cum[0] = 0;
     }
     __syncthreads();
-    const int n_tail = hist[0] + hist[66 + 0];   // offset of the last bucket + its count
-    __syncthreads();
-    // stable scatter (sequence order inside a bucket): every CTA must build the SAME order, so
-    // no atomics here - warp 0 walks the sequences 32 at a time and ranks equal buckets by lane
-    if (warp == 0) {
-      for (int base = 0; base < p.num_seqs; base += 32) {
-        const int s = base + lane;
-        int b = -1;
-        if (s < p.num_seqs) {
-          const int c = p.context_lens[s];          // L1 hit: read a moment ago
-          const int rem = c % part_tokens;
-          if (rem != 0 || c == 0) b = tail_bucket(c, rem, part_tokens, BS);
-        }
-        const unsigned same = __match_any_sync(0xffffffffu, b);
-        const int leader = __ffs(same) - 1;
-        const int rank = __popc(same & ((1u << lane) - 1u));
-        int start = 0;
-        if (b >= 0 && lane == leader) {
-          start = hist[66 + b];
-          hist[66 + b] = start + __popc(same);
-        }
-        start = __shfl_sync(0xffffffffu, start, leader);
-        if (b >= 0) tail_order[start + rank] = (unsigned short)s;
-        __syncwarp();
+    const int n_tail = hist[4 * NB];
+    // stable scatter: a warp's sequences in order, equal buckets ranked by lane
+    for (int ch = chunk0; ch < chunk1; ++ch) {
+      const int s = ch * 32 + lane;
+      int bkt = -1;
+      if (s < p.num_seqs) {
+        const int c = p.context_lens[s];            // L1 hit: read a moment ago
+        const int rem = c % part_tokens;
+        if (rem != 0 || c == 0) bkt = tail_bucket(c, rem, part_tokens, BS);
       }
+      const unsigned same = __match_any_sync(0xffffffffu, bkt);
+      const int leader = __ffs(same) - 1;
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      int start = 0;
+      if (bkt >= 0 && lane == leader) {
+        start = my_hist[bkt];
+        my_hist[bkt] = start + __popc(same);
+      }
+      start = __shfl_sync(0xffffffffu, start, leader);
+      if (bkt >= 0) tail_order[start + rank] = (unsigned short)s;
+      __syncwarp();
     }
     __syncthreads();
     plan.cum = cum;
@@ -795,7 +834,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
   // otherwise sit between the end of the previous kernel and the first KV request.
   Item cur, nxt;
   nxt.valid = 0;
-  int pend = fetch_id(p, lane);
+  int pend = blockIdx.x * nwarps + warp;      // lane 0's value is the one claim() broadcasts
   bool pend_valid = false, nxt_ready = false;
   claim(cur, pend, p, plan, total_items, part_blocks, BS, lane);
   pdl_wait();
@@ -805,7 +844,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
   pump(cur);
   auto advance = [&]() {
     if (!nxt_ready) {
-      if (!pend_valid) pend = fetch_id(p, lane);
+      if (!pend_valid) pend = fetch_id(p, lane, total_warps);
       claim(nxt, pend, p, plan, total_items, part_blocks, BS, lane);
     }
     cur = nxt;
@@ -924,7 +963,7 @@ __global__ void __launch_bounds__(128, min_ctas_per_sm<T, CT, GT, MMA>()) paged_
     for (int tile = 0; tile < ntiles;) {
       const int nt = (NTP == 2 && ntiles - tile >= 2) ? 2 : 1;
       if (!pend_valid && !nxt_ready && ntiles - tile <= S + 2) {
-        pend = fetch_id(p, lane);
+        pend = fetch_id(p, lane, total_warps);
         pend_valid = true;
       } else if (pend_valid && !nxt_ready && cur.issued >= ntiles) {
         claim(nxt, pend, p, plan, total_items, part_blocks, BS, lane);

@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(kGemm2Threads, 1)
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+        // m fastest: the CTAs working at the same time share W tiles (the lm_head at 256 rows has
+        // two M tiles per 128 vocabulary rows - with n fastest the 262 MB weight matrix would
+        // stream from HBM twice)
+        const int m0 = (tile % num_m) * kBM, n0 = (tile / num_m) * BN;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kGemm2Threads, 1)
     const unsigned char* slab_gen = gen + (slab - base);
     int t = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
-      const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+      const int m0 = (tile % num_m) * kBM, n0 = (tile / num_m) * BN;
       const int buf = t & 1;
       mbar_wait(tfull0 + 8 * buf, (t >> 1) & 1);
       tc_fence_after();
@@ -855,7 +858,18 @@ static int gemm(const void* A, const void* W, void* D, const void* bias, const v
              VLTR_ERR_INVALID, "opt_gemm: operands must be 16-byte aligned");
   // wide tiles when they still give every SM a CTA, else narrow ones
   const int tiles128 = ((N + 127) / 128) * ((M + kBM - 1) / kBM);
-  const bool wide = tiles128 >= num_sms();
+  bool wide = tiles128 >= num_sms();
+  if (wide && M <= 2 * kBM) {
+    // few rows (the lm_head of a decode step): the GEMM streams W once and is bound by HBM, so
+    // what matters is that the last wave of tiles is full - 32000 x 4096 at 256 rows is 500 wide
+    // tiles = 3.4 waves (84 % of 4), but 1000 narrow ones = 6.8 waves (97 % of 7)
+    const long long sms = num_sms();
+    auto fill = [&](int bn) {
+      const long long t = (long long)((N + bn - 1) / bn) * ((M + kBM - 1) / kBM);
+      return (double)t / (double)(((t + sms - 1) / sms) * sms);
+    };
+    if (fill(64) > fill(128) + 0.05) wide = false;
+  }
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, kBM, dtype);
   if (rc) return rc;

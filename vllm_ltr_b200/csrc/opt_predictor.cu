@@ -858,18 +858,10 @@ static int gemm(const void* A, const void* W, void* D, const void* bias, const v
              VLTR_ERR_INVALID, "opt_gemm: operands must be 16-byte aligned");
   // wide tiles when they still give every SM a CTA, else narrow ones
   const int tiles128 = ((N + 127) / 128) * ((M + kBM - 1) / kBM);
-  bool wide = tiles128 >= num_sms();
-  if (wide && M <= 2 * kBM) {
-    // few rows (the lm_head of a decode step): the GEMM streams W once and is bound by HBM, so
-    // what matters is that the last wave of tiles is full - 32000 x 4096 at 256 rows is 500 wide
-    // tiles = 3.4 waves (84 % of 4), but 1000 narrow ones = 6.8 waves (97 % of 7)
-    const long long sms = num_sms();
-    auto fill = [&](int bn) {
-      const long long t = (long long)((N + bn - 1) / bn) * ((M + kBM - 1) / kBM);
-      return (double)t / (double)(((t + sms - 1) / sms) * sms);
-    };
-    if (fill(64) > fill(128) + 0.05) wide = false;
-  }
+  // (narrow tiles for few rows to fill the last wave were tried for the lm_head - 1000 instead of
+  // 500 tiles for 32000 x 4096 at 256 rows - and measured slower, 106 vs 84 us: every tile
+  // re-reads its A rows, profiles/r02_lm_head.txt)
+  const bool wide = tiles128 >= num_sms();
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, kBM, dtype);
   if (rc) return rc;

@@ -1000,7 +1000,9 @@ def _main(out):
                     "(torch.matmul -> cuBLAS, bf16, seeded random weights, one set per layer) "
                     "between the ops, replayed from a CUDA graph; no embedding, lm_head, sampler "
                     "or scheduler tick", "finite": bool(torch.isfinite(out2.float()).all())}
-    if rank == 0 and not args.no_cpu_baseline:
+    # (N=1 only: under torchrun the other ranks would wait in the next collective, and torchrun
+    # pins OMP_NUM_THREADS=1, which is not the host the baseline is quoted on)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tps, cms, desc, cores, kind = cpu_reference_run(args, bench_shape, ctx, 2, 1,
                                                         args.cpu_sample_layers,
                                                         args.cpu_sample_batch)

@@ -4,7 +4,8 @@
 Metric (BASELINE.json): output tokens/s on a ShareGPT-shaped trace.  One "step" = one engine
 decode step of the hot path for a batch of B running sequences (one new token each): for every
 decoder layer  fused_add_rms_norm -> rotary_embedding -> reshape_and_cache -> paged_attention ->
-fused_add_rms_norm -> silu_and_mul, then the final norm (tools/hotpath.py; the cuBLAS
+fused_add_rms_norm -> silu_and_mul, then the final norm (tools/hotpath.py; in our arm the rotary
+embedding and the cache append are one launch, csrc/rope_cache.cu; the cuBLAS
 GEMMs between them are library code outside this path and are NOT executed or counted).
 Contexts are the running contexts of a synthetic ShareGPT-shaped trace.
 

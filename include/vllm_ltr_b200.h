@@ -110,6 +110,25 @@ int vltr_reshape_and_cache(const void* key, const void* value, void* key_cache,
                            int64_t key_stride, int64_t value_stride, int dtype, int kv_fp8,
                            float kv_scale, void* stream);
 
+/* ---- rotary embedding fused with the KV-cache append (behind the attention seam) ------------------
+ * = vltr_rotary_embedding(positions, query, key, ..., is_neox) followed by
+ *   vltr_reshape_and_cache(key, value, key_cache, value_cache, slot_mapping, ...)
+ * in ONE launch: replaces the pair ops.rotary_embedding (csrc/pos_encoding_kernels.cu:124-172,
+ * called from RotaryEmbedding.forward, vllm/model_executor/layers/rotary_embedding.py:136-158, via
+ * llama.py:159) + cache_ops.reshape_and_cache (csrc/cache_kernels.cu:235-276, called from
+ * flash_attn.py:192).  query [T, Hq, D] and key [T, Hkv, D] are rotated IN PLACE (row strides in
+ * elements), value [T, Hkv, D] is read, the caches have the paged layouts above; padding tokens
+ * (slot < 0) are rotated but not cached.  Bit-identical to the two separate calls.  Only NeoX
+ * rotation over the whole head (rot_dim == head_size) with 16-byte aligned operands is fused:
+ * anything else returns VLTR_ERR_UNSUPPORTED and the caller issues the two ops. */
+int vltr_rotary_embedding_and_cache(const int64_t* positions, void* query, void* key,
+                                    const void* value, void* key_cache, void* value_cache,
+                                    const int64_t* slot_mapping, const void* cos_sin_cache,
+                                    int64_t num_tokens, int num_heads, int num_kv_heads,
+                                    int head_size, int rot_dim, int is_neox, int64_t query_stride,
+                                    int64_t key_stride, int64_t value_stride, int block_size, int x,
+                                    int dtype, int kv_fp8, void* stream);
+
 /* copy_blocks (:97-152): key_cache_ptrs/value_cache_ptrs are HOST arrays of num_layers device
  * pointers; block_mapping is a HOST array of num_pairs (src,dst) int64 pairs in the reference's
  * std::map iteration order.  block_bytes = bytes of one block of one layer's K (== V).

@@ -84,6 +84,61 @@ def test_attention_backend_seam(monkeypatch):
                              decode_metadata=None), 1.0)
 
 
+def test_deferred_rotary(monkeypatch):
+    """The rotary embedding of a decoder layer is deferred into the layer's B200AttentionImpl
+    (fused with the cache append): install() wraps NeoX full-head RotaryEmbeddings that sit next
+    to an Attention layer, leaves everything else alone, and the cache-less profiling run still
+    rotates through the reference op."""
+    import torch
+    R.import_reference()
+    monkeypatch.setattr(torch.cuda, "get_device_capability", lambda *a: (10, 0))
+    from vllm.attention.layer import Attention
+    from vllm.model_executor.layers.rotary_embedding import RotaryEmbedding
+
+    from vllm_ltr_b200 import attention_backend as ab
+
+    class Layer(torch.nn.Module):
+        def __init__(self, neox=True, rot=128):
+            super().__init__()
+            self.rotary_emb = RotaryEmbedding(128, rot, 64, 10000, neox)
+            self.attn = Attention(32, 128, 0.088, num_kv_heads=8)
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l0, self.l1, self.l2 = Layer(), Layer(neox=False), Layer(rot=64)
+
+    torch.set_default_dtype(torch.float16)
+    try:
+        m = Model()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    real = m.l0.rotary_emb
+    assert ab.install(m) == 3
+    assert isinstance(m.l0.rotary_emb, ab.DeferredRotary) and m.l0.rotary_emb.inner is real
+    assert isinstance(m.l1.rotary_emb, RotaryEmbedding)      # GPT-J style: not fused
+    assert isinstance(m.l2.rotary_emb, RotaryEmbedding)      # partial rotation: not fused
+    assert "rotary_emb.inner.cos_sin_cache" not in "".join(m.state_dict().keys())
+    assert ab.install(m) == 0 and m.l0.rotary_emb.inner is real      # idempotent
+    ab.install(m, fuse_rope=False)
+    # deferral: q / k come back untouched, the impl holds (positions, module) for its next forward
+    pos = torch.arange(3)
+    q, k = torch.randn(3, 32 * 128), torch.randn(3, 8 * 128)
+    dr = ab.DeferredRotary(real, m.l0.attn.impl)
+    q2, k2 = dr(pos, q, k)
+    assert q2 is q and k2 is k and m.l0.attn.impl._pending_rope[1] is real
+    # the profiling run (no KV cache): rotation through the reference op, then the reference impl
+    seen = []
+    monkeypatch.setattr(real, "forward", lambda p_, q_, k_, o_=None: seen.append("rope") or (q_, k_))
+    m.l0.attn.impl.reference_impl = __import__("types").SimpleNamespace(
+        forward=lambda *a: seen.append("ref") or "out")
+    assert m.l0.attn.impl.forward(q, k, k, None, None, 1.0) == "out"
+    assert seen == ["rope", "ref"] and m.l0.attn.impl._pending_rope is None
+    # offsets (batched LoRA form) are not deferred
+    dr(pos, q, k, torch.zeros(3, dtype=torch.long))
+    assert seen == ["rope", "ref", "rope"] and m.l0.attn.impl._pending_rope is None
+
+
 def test_logits_processor_seam(monkeypatch):
     """f3 (logits half): ``logits.install`` re-binds ``LogitsProcessor._get_logits``; the host
     logic around the matmul (bias, gather, vocabulary trim, None on non-driver ranks) is the

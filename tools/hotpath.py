@@ -128,6 +128,8 @@ class DecodeHotPath:
         # C: the extension module to drive.  Always vllm_ltr_b200._C in the product; bench.py's
         # reference arm passes the reference's own CPU build of vllm._C (same surface) instead.
         self.C = _default_C() if C is None else C
+        # rope + cache append as one launch: only with the product's own extension
+        self.fuse_rope_cache = C is None or getattr(C, "__name__", "").startswith("vllm_ltr_b200")
         self.shape = s = shape
         self.device = device
         self.layers = s.layers if layers is None else layers
@@ -174,6 +176,22 @@ class DecodeHotPath:
         self.scale = float(scale)
         self.attn_events = None   # optional [(start, end)] CUDA events around each attention call
         self.gemm_w = None        # optional per-layer GEMM weights (enable_gemms)
+
+    def _rope_and_cache(self, positions, q, k, v, kc, vc, slot_mapping, T) -> None:
+        """rotary_emb + the cache append of Attention.forward (llama.py:159, flash_attn.py:192):
+        one fused launch behind the attention seam (vllm_ltr_b200.attention_backend) when this
+        path drives the product's kernels, the reference's two ops otherwise (``fuse_rope_cache``
+        False: the reference extension modules, or an A/B run)."""
+        s = self.shape
+        if self.fuse_rope_cache:
+            from vllm_ltr_b200.attention_backend import rotary_embedding_and_cache
+            if rotary_embedding_and_cache(positions, q, k, v, kc, vc, slot_mapping, s.head_size,
+                                          self.cos_sin, True, s.kv_cache_dtype):
+                return
+        self.C.ops.rotary_embedding(positions, q, k, s.head_size, self.cos_sin, True)
+        self.C.cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
+                                           v.view(T, s.kv_heads, s.head_size), kc, vc,
+                                           slot_mapping, s.kv_cache_dtype, 1.0)
 
     def enable_gemms(self, seed: int = 1) -> None:
         """Context for the hot-path numbers: also run the four dense projections of every layer
@@ -256,11 +274,8 @@ class DecodeHotPath:
             else:
                 # previous down_proj exchange + this layer's input_layernorm
                 comm.allreduce_add_rms_norm(1, self.norm_w[2 * layer], s.eps, T)
-            ops.rotary_embedding(positions, q, k, s.head_size, self.cos_sin, True)
             kc, vc = self.key_caches[layer], self.value_caches[layer]
-            cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
-                                        v.view(T, s.kv_heads, s.head_size), kc, vc, slot_mapping,
-                                        s.kv_cache_dtype, 1.0)
+            self._rope_and_cache(positions, q, k, v, kc, vc, slot_mapping, T)
             ev = self.attn_events
             if ev is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -306,11 +321,8 @@ class DecodeHotPath:
             gw = self.gemm_w[layer] if self.gemm_w is not None else None
             if gw is not None:
                 torch.matmul(self.normed[:T] if layer == 0 else hidden, gw[0].t(), out=qkv)
-            ops.rotary_embedding(positions, q, k, s.head_size, self.cos_sin, True)
             kc, vc = self.key_caches[layer], self.value_caches[layer]
-            cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
-                                        v.view(T, s.kv_heads, s.head_size), kc, vc, slot_mapping,
-                                        s.kv_cache_dtype, 1.0)
+            self._rope_and_cache(positions, q, k, v, kc, vc, slot_mapping, T)
             ev = self.attn_events
             if ev is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -14,11 +14,66 @@ reference's FlashAttention backend's, unchanged (same wire format, model_runner.
 This is also where a fused cache-append + attention kernel plugs in: ``forward`` is the one place
 that sees key / value, the slot mapping and the block tables of a step together.
 """
+import ctypes
 from typing import Dict, List, Optional, Tuple, Type
 
 import torch
 
+from ._lib import check, declare, lib
+
 _PARTITION_SIZE = 512            # vllm/attention/ops/paged_attn.py:10
+_P = ctypes.c_void_p
+declare("vltr_rotary_embedding_and_cache", ctypes.c_int,
+        [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+         ctypes.c_int, ctypes.c_int, ctypes.c_int, _P])
+_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_ERR_UNSUPPORTED = 3             # include/vllm_ltr_b200.h
+
+
+def rotary_embedding_and_cache(positions: torch.Tensor, query: torch.Tensor, key: torch.Tensor,
+                               value: torch.Tensor, key_cache: torch.Tensor,
+                               value_cache: torch.Tensor, slot_mapping: torch.Tensor,
+                               head_size: int, cos_sin_cache: torch.Tensor, is_neox: bool,
+                               kv_cache_dtype: str = "auto") -> bool:
+    """``ops.rotary_embedding(positions, query, key, head_size, cos_sin_cache, is_neox)`` followed
+    by ``cache_ops.reshape_and_cache(key, value, key_cache, value_cache, slot_mapping, ...)`` in
+    one launch (csrc/rope_cache.cu).  query [T, Hq*D] / key, value [T, Hkv*D] (or 3-D views) with
+    unit element stride inside a row; query and key are rotated in place.  Returns False - and
+    touches nothing - when the shapes are outside the fused form (the caller issues the two ops);
+    other errors raise."""
+    if not query.is_cuda:
+        raise RuntimeError("vllm_ltr_b200: tensors must be on a CUDA device (no CPU path)")
+    code = _DTYPE.get(query.dtype)
+    if code is None or key.dtype != query.dtype or value.dtype != query.dtype or \
+            cos_sin_cache.dtype != query.dtype:
+        return False
+    if kv_cache_dtype not in ("auto", "fp8"):
+        raise RuntimeError(f"Unsupported data type of kv cache: {kv_cache_dtype}")
+    fp8 = 1 if kv_cache_dtype == "fp8" else 0
+    if positions.dtype != torch.int64 or slot_mapping.dtype != torch.int64 or \
+            not positions.is_contiguous() or not slot_mapping.is_contiguous():
+        return False
+    T = query.shape[0]
+    Hq = query.numel() // (T * head_size) if T else 0
+    Hkv = key.numel() // (T * head_size) if T else 0
+    if T == 0:
+        return True
+    if positions.numel() != T or slot_mapping.numel() != T or \
+            query.stride(-1) != 1 or key.stride(-1) != 1 or value.stride(-1) != 1:
+        return False
+    rot_dim = cos_sin_cache.shape[1]
+    with torch.cuda.device(query.device):
+        rc = lib.vltr_rotary_embedding_and_cache(
+            positions.data_ptr(), query.data_ptr(), key.data_ptr(), value.data_ptr(),
+            key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr(),
+            cos_sin_cache.data_ptr(), T, Hq, Hkv, head_size, rot_dim, 1 if is_neox else 0,
+            query.stride(0), key.stride(0), value.stride(0), key_cache.size(3), key_cache.size(4),
+            code, fp8, torch._C._cuda_getCurrentRawStream(query.device.index))
+    if rc == _ERR_UNSUPPORTED:
+        return False
+    check(rc)
+    return True
 
 _classes = None
 
@@ -57,13 +112,19 @@ def backend_classes():
                 raise ValueError(f"Head size {head_size} is not supported by PagedAttention.")
             # only for the memory-profiling run, which has no KV cache (model_runner.py:863-869)
             self.reference_impl = reference_impl
+            # (positions, RotaryEmbedding) left by a DeferredRotary in front of this layer: the
+            # rotation is applied here, fused with the cache append
+            self._pending_rope = None
 
         def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
                     kv_cache: Optional[torch.Tensor], attn_metadata, kv_scale: float) -> torch.Tensor:
+            rope, self._pending_rope = self._pending_rope, None
             if kv_cache is None:
                 if self.reference_impl is None:
                     raise RuntimeError("B200AttentionImpl needs a KV cache (the cache-less "
                                        "profiling run belongs to the reference impl)")
+                if rope is not None:
+                    rope[1](rope[0], query, key)
                 return self.reference_impl.forward(query, key, value, kv_cache, attn_metadata,
                                                    kv_scale)
             num_tokens, hidden = query.shape
@@ -73,9 +134,21 @@ def backend_classes():
             v = value.view(-1, Hkv, D)
             key_cache, value_cache = PagedAttention.split_kv_cache(kv_cache, Hkv, D)
             kvd = attn_metadata.kv_cache_dtype
-            # a3: append this step's keys / values (flash_attn.py:185-196)
-            _C.cache_ops.reshape_and_cache(k, v, key_cache, value_cache,
-                                           attn_metadata.slot_mapping.flatten(), kvd, kv_scale)
+            # a6 + a3: rotate this step's queries / keys (when a DeferredRotary handed the
+            # rotation over) and append keys / values to the cache (flash_attn.py:185-196) - one
+            # launch; the two reference ops when the shapes are outside the fused form
+            slots = attn_metadata.slot_mapping.flatten()
+            fused = False
+            if rope is not None:
+                positions, rot = rope
+                rot.cos_sin_cache = rot.cos_sin_cache.to(positions.device)   # rotary_embedding.py:143
+                fused = rotary_embedding_and_cache(positions, q, k, v, key_cache, value_cache,
+                                                   slots, D, rot.cos_sin_cache,
+                                                   rot.is_neox_style, kvd)
+                if not fused:
+                    rot(positions, query, key)
+            if not fused:
+                _C.cache_ops.reshape_and_cache(k, v, key_cache, value_cache, slots, kvd, kv_scale)
             npre = attn_metadata.num_prefill_tokens
             ndec = attn_metadata.num_decode_tokens
             assert k.shape[0] == npre + ndec
@@ -146,12 +219,50 @@ def backend_classes():
     return _classes
 
 
-def install(model: torch.nn.Module) -> int:
-    """Give every ``Attention`` layer of a built model a ``B200AttentionImpl``.  Returns the
-    number of layers switched."""
+class DeferredRotary(torch.nn.Module):
+    """Stands where a decoder layer keeps its ``rotary_emb`` (llama.py:139-147, called at :159
+    right before ``self.attn``): instead of launching ``ops.rotary_embedding`` it hands
+    (positions, the real module) to the layer's ``B200AttentionImpl``, whose ``forward`` - the
+    very next call - rotates queries and keys in place while appending to the KV cache
+    (csrc/rope_cache.cu).  Calls the fused kernel cannot serve (per-token offsets of the batched
+    LoRA form) go straight to the real module."""
+
+    def __init__(self, inner: torch.nn.Module, impl) -> None:
+        super().__init__()
+        self.inner = inner
+        self._impl = [impl]              # in a list: not a submodule, not in state_dict
+
+    def forward(self, positions, query, key, offsets=None):
+        if offsets is not None:
+            return self.inner(positions, query, key, offsets)
+        self._impl[0]._pending_rope = (positions, self.inner)
+        return query, key
+
+
+def install(model: torch.nn.Module, fuse_rope: bool = True) -> int:
+    """Give every ``Attention`` layer of a built model a ``B200AttentionImpl`` and, with
+    ``fuse_rope``, defer the rotary embedding of its decoder layer into it.  Returns the number
+    of layers switched."""
     from vllm.attention.layer import Attention
     backend, impl_cls = backend_classes()
     n = 0
+    if fuse_rope:
+        from vllm.model_executor.layers.rotary_embedding import RotaryEmbedding
+        for parent in model.modules():
+            rot = getattr(parent, "rotary_emb", None)
+            att = getattr(parent, "attn", None)
+            if isinstance(att, Attention) and isinstance(rot, RotaryEmbedding) and \
+                    type(rot).forward is RotaryEmbedding.forward and rot.is_neox_style and \
+                    rot.rotary_dim == rot.head_size:
+                if not isinstance(att.impl, impl_cls):
+                    old = att.impl
+                    sw = getattr(old, "sliding_window", None)
+                    att.impl = impl_cls(old.num_heads, old.head_size, old.scale, old.num_kv_heads,
+                                        old.alibi_slopes, None if sw in (None, (-1, -1)) else sw,
+                                        reference_impl=old)
+                    att.backend = backend
+                    n += 1
+                parent.rotary_emb = DeferredRotary(rot, att.impl)
     for mod in model.modules():
         if isinstance(mod, Attention) and not isinstance(mod.impl, impl_cls):
             old = mod.impl

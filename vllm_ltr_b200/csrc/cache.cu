@@ -29,14 +29,6 @@ namespace vltr {
 // ------------------------------------------------------------------------------------------------
 // reshape_and_cache
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename CT, bool FP8>
-__device__ __forceinline__ CT cache_cvt(T v) {
-  if constexpr (FP8)
-    return to_fp8<T>(v);
-  else
-    return v;
-}
-
 // vector path: one warp per (token, head) row; the warp of the FIRST token of a run does the work.
 //   A run = consecutive tokens whose slots are consecutive inside one KV block - what every
 //   prefill chunk produces (block_size tokens per block), while decode tokens are runs of one.

@@ -185,6 +185,29 @@ __device__ __forceinline__ __nv_bfloat16 from_fp8<__nv_bfloat16>(uint8_t a) {
   return __float2bfloat16(__half2float(fp8_to_half(a)));
 }
 
+// ---- helpers shared by pos_encoding.cu, cache.cu and rope_cache.cu --------------------------------
+// one rotary pair "in T" (pos_encoding_kernels.cu:34-38: every * and +/- rounds to T)
+template <typename T>
+__device__ __forceinline__ void rot_pair(T& x, T& y, T c, T s) {
+  const float fx = ST<T>::to_f(x), fy = ST<T>::to_f(y), fc = ST<T>::to_f(c), fs = ST<T>::to_f(s);
+  if constexpr (sizeof(T) == 4) {
+    x = fx * fc - fy * fs;
+    y = fy * fc + fx * fs;
+  } else {
+    x = ST<T>::from_f(rt<T>(fx * fc) - rt<T>(fy * fs));
+    y = ST<T>::from_f(rt<T>(fy * fc) + rt<T>(fx * fs));
+  }
+}
+
+// element on its way into the KV cache: as is, or e5m2 (saturate to finite)
+template <typename T, typename CT, bool FP8>
+__device__ __forceinline__ CT cache_cvt(T v) {
+  if constexpr (FP8)
+    return to_fp8<T>(v);
+  else
+    return v;
+}
+
 }  // namespace vltr
 
 // dtype dispatch over the three activation types

@@ -14,18 +14,6 @@
 
 namespace vltr {
 
-template <typename T>
-__device__ __forceinline__ void rot_pair(T& x, T& y, T c, T s) {
-  const float fx = ST<T>::to_f(x), fy = ST<T>::to_f(y), fc = ST<T>::to_f(c), fs = ST<T>::to_f(s);
-  if constexpr (sizeof(T) == 4) {
-    x = fx * fc - fy * fs;
-    y = fy * fc + fx * fs;
-  } else {
-    x = ST<T>::from_f(rt<T>(fx * fc) - rt<T>(fy * fs));
-    y = ST<T>::from_f(rt<T>(fy * fc) + rt<T>(fx * fs));
-  }
-}
-
 // NeoX, vectorised.  item = ((token * (Hq+Hkv)) + head) * chunks + chunk
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -52,6 +52,9 @@ pair) stage "two KV blocks per iteration: default build (e5m2 only) vs PAIR=2 bu
   tail -4 $O/pytest_attn.log
   VLTR_LIB=$P2 timeout 900 python -m pytest tests/test_gpu_attention.py -x -q -m gpu -p no:cacheprovider > $O/pytest_attn_p2.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   tail -4 $O/pytest_attn_p2.log;;
+ropetests) stage "fused rope + cache tests, hot-path tests"
+  timeout 900 python -m pytest tests/test_gpu_rope_cache.py tests/test_gpu_hotpath.py tests/test_gpu_cache.py -x -q -m gpu -p no:cacheprovider > $O/pytest_rope.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  tail -6 $O/pytest_rope.log;;
 chain) stage "chain bench"
   timeout 600 python tools/chain_bench.py --model llama-2-7b > $O/chain_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   timeout 600 python tools/chain_bench.py --model llama-3-8b >> $O/chain_bench.log 2>&1

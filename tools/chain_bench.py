@@ -84,11 +84,23 @@ def main():
         def rope():
             _C.ops.rotary_embedding(inp["positions"], q, k, s.head_size, hp.cos_sin, True)
 
+        clayer = [0]
+
         def reshape():
+            # every decoder layer appends to its OWN cache: rotate, or the destination sectors
+            # of the previous launch are still in L2 and the op looks twice as fast as it is
+            i = clayer[0] = (clayer[0] + 1) % hp.layers
             _C.cache_ops.reshape_and_cache(k.view(T, s.kv_heads, s.head_size),
-                                           v.view(T, s.kv_heads, s.head_size), hp.key_caches[0],
-                                           hp.value_caches[0], inp["slot_mapping"],
+                                           v.view(T, s.kv_heads, s.head_size), hp.key_caches[i],
+                                           hp.value_caches[i], inp["slot_mapping"],
                                            s.kv_cache_dtype, 1.0)
+
+        def rope_cache():
+            from vllm_ltr_b200.attention_backend import rotary_embedding_and_cache
+            i = clayer[0] = (clayer[0] + 1) % hp.layers
+            assert rotary_embedding_and_cache(inp["positions"], q, k, v, hp.key_caches[i],
+                                              hp.value_caches[i], inp["slot_mapping"], s.head_size,
+                                              hp.cos_sin, True, s.kv_cache_dtype)
 
         def silu():
             _C.ops.silu_and_mul(hp.act_out[:T], hp.gate_up[:T])
@@ -98,6 +110,10 @@ def main():
             "rotary_embedding": (rope, T * (s.q_heads + s.kv_heads) * s.head_size * es * 2
                                  + T * s.head_size * es + 8 * T),
             "reshape_and_cache": (reshape, T * 2 * s.kv_heads * s.head_size * (es + cs) + 8 * T),
+            "rope + cache append (fused)": (rope_cache,
+                                            T * 2 * s.q_heads * s.head_size * es
+                                            + T * s.kv_heads * s.head_size * (3 * es + 2 * cs)
+                                            + T * s.head_size * es + 16 * T),
             "silu_and_mul": (silu, T * s.inter * es * 3),
             "paged_attention": (attn, int(ctx.sum()) * 2 * s.kv_heads * s.head_size * cs
                                 + 2 * T * s.q_heads * s.head_size * es),
@@ -117,18 +133,26 @@ def main():
                 res.append(graph_time(fn, args.n))
             tune("pdl", 1)
             floor = byts / peak / 1e3
-            print(f"   {op:20s} {res[0]:7.2f} us/launch (no PDL {res[1]:7.2f})   algorithmic "
+            print(f"   {op:28s} {res[0]:7.2f} us/launch (no PDL {res[1]:7.2f})   algorithmic "
                   f"{byts/1e6:8.2f} MB = {floor:6.2f} us at {peak:.0f} GB/s  ({floor/res[0]*100:4.0f}%)",
                   flush=True)
             rows.append(dict(model=name, op=op, us=res[0], us_nopdl=res[1], bytes=byts))
+        def layer_small_fused():
+            rms(); rope_cache(); rms(); silu()
+
+        def layer_full_fused():
+            rms(); rope_cache(); attn(); rms(); silu()
+
         for label, fn in (("layer without attention (5 kernels)", layer_small),
-                          ("layer (6 kernels)", layer_full)):
+                          ("layer (6 kernels)", layer_full),
+                          ("layer without attention, rope+cache fused (4)", layer_small_fused),
+                          ("layer, rope+cache fused (5 kernels)", layer_full_fused)):
             res = []
             for pdl in (1, 0):
                 tune("pdl", pdl)
                 res.append(graph_time(fn, 16) )
             tune("pdl", 1)
-            print(f"   {label:38s} {res[0]:7.2f} us (no PDL {res[1]:7.2f})", flush=True)
+            print(f"   {label:46s} {res[0]:7.2f} us (no PDL {res[1]:7.2f})", flush=True)
             rows.append(dict(model=name, op=label, us=res[0], us_nopdl=res[1]))
         del hp
         torch.cuda.empty_cache()

@@ -63,6 +63,13 @@ chain) stage "chain bench"
 cache) stage "reshape_and_cache bench"
   timeout 600 python tools/cache_bench.py --json $O/cache_bench.json > $O/cache_bench.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   cat $O/cache_bench.log;;
+ncufinal) stage "ncu --set full: e5m2 and bf16 GQA attention, fused rope+cache"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 4 -c 1 -f -o $O/attn_fp8_final python tools/attn_tune.py --cases 8b-gqa-fp8:256:trace > $O/ncu_attn_fp8.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  export_rep attn_fp8_final
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 4 -c 1 -f -o $O/attn_gqa_final python tools/attn_tune.py --cases 8b-gqa-bf16:256:trace > $O/ncu_attn_gqa.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  export_rep attn_gqa_final
+  timeout 600 ncu --set full --clock-control none -k regex:rope_and_cache -s 8 -c 2 -f -o $O/rope_cache_prof python tools/chain_bench.py --model llama-2-7b --n 8 > $O/ncu_rope_cache.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
+  export_rep rope_cache_prof;;
 ncu) stage "ncu: e5m2 attention, reshape_and_cache"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attention_kernel -s 4 -c 1 -f -o $O/attn_fp8_prof python tools/attn_tune.py --cases 8b-gqa-fp8:256:trace > $O/ncu_attn_fp8.log 2>&1; echo "rc=$?" | tee -a $O/session3.log
   export_rep attn_fp8_prof

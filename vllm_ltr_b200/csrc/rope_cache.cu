@@ -77,11 +77,15 @@ __global__ void __launch_bounds__(256)
   const int64_t row = (int64_t)((int)blockIdx.x - q_ctas) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t num_rows = (int64_t)num_tokens * num_kv_heads;
   const int64_t token = row < num_rows ? row / num_kv_heads : 0;
-  int64_t slot = -1, prev = -2;
+  int64_t slot = -1, prev = -2, pos_l = 0;
   int n = 0;
   if (row < num_rows) {
     slot = slot_mapping[token];
     if (token > 0) prev = slot_mapping[token - 1];
+    // positions of the run's tokens, one per lane (a run is at most block_size <= 32 tokens):
+    // step inputs like the slots, fetched ahead of the wait - the rotation's cos / sin row
+    // depends on them
+    if (token + lane < num_tokens) pos_l = positions[token + lane];
     const int room = block_size - (int)(slot % block_size);
     const bool cont = lane > 0 && lane < room && token + lane < num_tokens &&
                       slot_mapping[token + lane] == slot + lane;
@@ -126,9 +130,12 @@ __global__ void __launch_bounds__(256)
     }
   }
   // K: (token of the run, chunk pair) over the lanes, consecutive lanes on consecutive tokens
-  for (int idx = lane; idx < rchunks * n; idx += 32) {
-    const int c = idx / n, i = idx - c * n;
-    const int64_t pos = positions[token + i];
+  for (int idx0 = 0; idx0 < rchunks * n; idx0 += 32) {      // warp-uniform trip count (shuffle inside)
+    const int idx = idx0 + lane;
+    const bool live = idx < rchunks * n;
+    const int c = live ? idx / n : 0, i = live ? idx - c * n : 0;
+    const int64_t pos = __shfl_sync(0xffffffffu, pos_l, i);
+    if (!live) continue;
     const T* cache = cos_sin_cache + pos * head_size + c * N;
     T* arr = kbase + (int64_t)i * key_stride + c * N;
     Vec16<T> x, y, cs, sn;

@@ -137,6 +137,16 @@ def run(n, seed, schedule_type, num_gpu_blocks, num_cpu_blocks, block_size=4, ma
             # i.e. in object-address order, so the free list is permuted run to run.  Sizes are.
             "block_tables": [sorted((k, len(v)) for k, v in m.block_tables.items())
                              for m in metas],
+            # everything else schedule() puts into the SequenceGroupMetadata (scheduler.py:1661-1678)
+            "meta": [(m.request_id, m.token_chunk_size,
+                      sorted((k, d.get_len(), d is s.seq_group.seqs_dict[k].data)
+                             for k, d in m.seq_data.items()),
+                      list(m.computed_block_nums), m.need_score, m.multi_modal_data is None,
+                      m.state is s.seq_group.state, m.sampling_params is s.seq_group.sampling_params,
+                      m.lora_request is None,
+                      s.seq_group.metrics.first_scheduled_time is not None,
+                      s.seq_group.metrics.time_in_queue is not None)
+                     for s, m in zip(outs.scheduled_seq_groups, metas)],
             "n_prefill": outs.num_prefill_groups,
             "n_tokens": outs.num_batched_tokens,
             "swap_in": len(outs.blocks_to_swap_in),

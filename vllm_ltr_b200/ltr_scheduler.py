@@ -78,19 +78,23 @@ def _ref():
 # ---------------------------------------------------------------------------------------------
 def get_opt_ordered_requests(self) -> list:
     # need_aux_model_score() is `aux_model_score is None` (vllm/sequence.py:460-461): read the
-    # attribute directly, the scan touches every waiting request every tick
-    unscored = [r for r in self.waiting if r.aux_model_score is None]
-    if unscored:
+    # attribute directly.  One pass gathers the waiting queue's scores (the sort needs them
+    # anyway); the list of unscored requests is only built on the ticks that have any.
+    live = list(self.waiting)
+    nw = len(live)
+    scores = [r.aux_model_score for r in live]
+    if None in scores:
+        unscored = [r for r, sc in zip(live, scores) if sc is None]
         timed = int(os.environ.get("OPT_TIME", 0))
         t0 = time.time() if timed else 0.0
         self.aux_model.obtain_aux_scores(unscored)
         if timed:
             print("OPT-TIME: ", time.time() - t0)
-    live = list(self.waiting)
-    nw = len(live)
+        scores = [r.aux_model_score for r in live]
     live.extend(self.running)
     nr = len(live) - nw
     live.extend(self.swapped)
+    scores.extend([r.aux_model_score for r in islice(live, nw, None)])
     pri = None
     if self.starv != -1:
         # starvation control: a request idle for `starv` ticks is promoted for `period`
@@ -101,7 +105,7 @@ def get_opt_ordered_requests(self) -> list:
             elif r.pri == -1 and r.runs <= 0:
                 r.pri = 0
         pri = [r.pri for r in live]
-    order = self._vltr_ranker.order([r.aux_model_score for r in live], pri, negate=True)
+    order = self._vltr_ranker.order(scores, pri, negate=True)
     n = len(live)
     if n >= 2:
         ordered = list(itemgetter(*order.tolist())(live))
@@ -385,6 +389,53 @@ def general_schedule(self):
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# schedule(): SequenceGroupMetadata of the scheduled requests      (scheduler.py:1622-1678)
+# ---------------------------------------------------------------------------------------------
+def schedule(self):
+    """``Scheduler.schedule`` for the configuration the LTR engine runs (no prefix caching, real
+    allocation): the same ``(seq_group_metadata_list, scheduler_outputs)``, object for object.
+    The reference calls, per scheduled request and per step, four block-manager methods that are
+    no-ops without prefix caching (``access_all_blocks_in_seq`` :1652, ``get_common_computed_
+    block_ids`` :1654 -> ``[]``, ``mark_blocks_as_computed`` :1690) and walks ``get_seqs`` twice;
+    here the loop reads what it needs directly.  With prefix caching or ``fake_allocate`` the
+    reference method runs unchanged."""
+    bm = self.block_manager
+    if getattr(bm, "enable_caching", False) or self.fake_allocate or \
+            not hasattr(bm, "block_tables"):
+        return self._vltr_ref_schedule()
+    S = _ref()
+    RUNNING = S.SequenceStatus.RUNNING
+    SGM = S.SequenceGroupMetadata
+    outs = self._schedule()
+    now = time.time()
+    tables = bm.block_tables
+    need_score = outs.need_score
+    any_prefill = outs.num_prefill_groups > 0
+    metadata = []
+    for ssg in outs.scheduled_seq_groups:
+        sg = ssg.seq_group
+        m = sg.metrics
+        if m.first_scheduled_time is None:          # maybe_set_first_scheduled_time (:1634)
+            m.first_scheduled_time = now
+            m.time_in_queue = now - m.arrival_time
+        seq_data = {}
+        block_tables = {}
+        for seq in sg.seqs_dict.values():
+            if seq.status == RUNNING:
+                sid = seq.seq_id
+                seq_data[sid] = seq.data
+                block_tables[sid] = [b.block_number for b in tables[sid]]
+        metadata.append(SGM(
+            request_id=sg.request_id, is_prompt=sg.is_prefill(), seq_data=seq_data,
+            sampling_params=sg.sampling_params, block_tables=block_tables,
+            token_chunk_size=ssg.token_chunk_size, lora_request=sg.lora_request,
+            computed_block_nums=[], state=sg.state,
+            multi_modal_data=sg.multi_modal_data if any_prefill else None,
+            need_score=need_score))
+    return metadata, outs
+
+
 def install(scheduler, ranker=None):
     """Bind the B200 LTR tick on a reference ``Scheduler`` whose schedule_type is "opt*".
     ``ranker`` is for tests of the host logic only (an object with ``order(scores, pri, negate)``);
@@ -396,4 +447,7 @@ def install(scheduler, ranker=None):
     scheduler._schedule = types.MethodType(general_schedule, scheduler)
     scheduler._get_ordered_requests = types.MethodType(get_opt_ordered_requests, scheduler)
     scheduler._update_priority = types.MethodType(update_opt_priority, scheduler)
+    if not hasattr(scheduler, "_vltr_ref_schedule"):
+        scheduler._vltr_ref_schedule = scheduler.schedule      # the reference's bound method
+    scheduler.schedule = types.MethodType(schedule, scheduler)
     return scheduler

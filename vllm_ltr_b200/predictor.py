@@ -17,6 +17,7 @@ epilogues, one stream, no host sync until the scores are read).
 import ctypes
 import json
 import os
+from itertools import chain
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -194,8 +195,10 @@ class OPTPredictor:
         self.max_batch_prompts = max_batch_prompts
         self._ws = None
         self._ws_cap = (0, 0)
-        self._host = None
-        self._host_evt = None
+        # pinned staging ring: the host packs batch k+1 (and k+2) while the copy of batch k waits
+        # on the stream behind the forward of batch k-1
+        self._stage = [[None, None] for _ in range(3)]        # [buffer, copy-done event]
+        self._stage_i = 0
         # single-prompt forwards (the steady-state tick scores one new prompt) replay a CUDA graph
         # per 64-token bucket: ~90 launches and 2 tensor-map encodes per dense layer become one
         # graph launch.  Keyed by padded token count; dropped when the workspace is reallocated.
@@ -310,24 +313,26 @@ class OPTPredictor:
         # one pinned staging buffer (persistent, grow-only), one H2D copy:
         # ids | positions | cu_seqlens | last_rows
         need = 2 * m + 2 * n + 1
-        if self._host is None or self._host.numel() < need:
-            self._host = torch.empty(max(need, 8192), dtype=torch.int32).pin_memory()
-        if self._host_evt is not None:
-            self._host_evt.synchronize()          # the previous copy out of the buffer is done
-        host = self._host[:need]
+        slot = self._stage[self._stage_i]
+        self._stage_i = (self._stage_i + 1) % len(self._stage)
+        if slot[1] is not None:
+            slot[1].synchronize()                 # the previous copy out of this buffer is done
+        if slot[0] is None or slot[0].numel() < need:
+            slot[0] = torch.empty(max(need, 8192), dtype=torch.int32).pin_memory()
+        host = slot[0][:need]
         ids, pos = host[:m], host[m:2 * m]
         cu, last = host[2 * m:2 * m + n + 1], host[2 * m + n + 1:]
         import numpy as np
         la = np.asarray(lens, dtype=np.int64)
         ends = np.cumsum(la)
-        ids.numpy()[:] = np.fromiter((t for p in batch for t in p), dtype=np.int32, count=m)
+        ids.numpy()[:] = np.fromiter(chain.from_iterable(batch), dtype=np.int32, count=m)
         pos.numpy()[:] = np.arange(m, dtype=np.int64) - np.repeat(ends - la, la)
         cu.numpy()[0] = 0
         cu.numpy()[1:] = ends
         last.numpy()[:] = ends - 1
         d = host.to(self.device, non_blocking=True)
-        self._host_evt = torch.cuda.Event()
-        self._host_evt.record()
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
         ws, ws_bytes = self._workspace(m, n)
         base = d.data_ptr()
         with torch.cuda.device(self.device):
@@ -337,26 +342,53 @@ class OPTPredictor:
                                        torch._C._cuda_getCurrentRawStream(self.device.index)))
         self._last_inputs = d   # keep alive until the stream has consumed it
 
-    def scores(self, prompts: Sequence[Sequence[int]], mtype: str = "reg") -> List[float]:
-        """What the reference hands to the scheduler: ``logits[:,0].tolist()`` after
-        compute_logits (opt.py:389-409) - for classification heads the argmax label as float."""
+    def score_column(self, prompts: Sequence[Sequence[int]]) -> torch.Tensor:
+        """``logits[:, 0]`` after compute_logits (opt.py:389-409; for classification heads the
+        argmax label as float) as a float32 tensor ON THE DEVICE: nothing here waits for the GPU,
+        so a caller can prepare the next batch on the host while this one runs."""
         lg = self.logits(prompts)
         if self.num_labels > 1:
             lg = lg[:, :self.num_labels].argmax(dim=-1, keepdim=True).float()
-        return lg[:, 0].tolist()
+        return lg[:, 0]
+
+    def scores(self, prompts: Sequence[Sequence[int]], mtype: str = "reg") -> List[float]:
+        """What the reference hands to the scheduler: ``logits[:,0].tolist()``."""
+        return self.score_column(prompts).tolist()
 
 
 class B200AuxModel:
     """``scheduler.aux_model``: any object with ``obtain_aux_scores(seq_groups) -> List[float]``
-    that calls ``set_aux_model_score`` on each group (aux_llm_engine.py:332-412)."""
+    that calls ``set_aux_model_score`` on each group (aux_llm_engine.py:332-412).
+
+    A burst of new requests (10 000 at t=0 in the synthetic trace) is scored in chunks of
+    ``chunk_prompts`` prompts: the forward of a chunk is only enqueued, so the GPU runs it while
+    the host tokenises and packs the next one; the scores are read back once, after the last
+    chunk (one device synchronisation per call, as before)."""
 
     def __init__(self, predictor: OPTPredictor, tokenizer: Callable[[str], List[int]],
                  max_length: int = 2048,
-                 batch_tokenizer: Optional[Callable[[List[str]], List[List[int]]]] = None):
+                 batch_tokenizer: Optional[Callable[[List[str]], List[List[int]]]] = None,
+                 chunk_prompts: int = 1024):
         self.predictor = predictor
         self.tokenizer = tokenizer
         self.batch_tokenizer = batch_tokenizer
         self.max_length = max_length
+        self.chunk_prompts = max(1, int(chunk_prompts))
+        self._pool = None
+
+    @staticmethod
+    def _batch_encoder(hf) -> Optional[Callable[[List[str]], List[List[int]]]]:
+        """Batch encoding with the ids ``hf.encode(text)`` gives one by one, tokenised in parallel
+        by the Rust backend.  With no truncation / padding configured on the backend tokenizer its
+        own ``encode_batch`` is what ``hf(texts)`` ends up calling
+        (PreTrainedTokenizerFast._batch_encode_plus) minus the BatchEncoding bookkeeping
+        (attention masks, type ids: ~40 % of the call at 10 000 prompts)."""
+        if not getattr(hf, "is_fast", False):
+            return None
+        raw = getattr(hf, "backend_tokenizer", None)
+        if raw is not None and raw.truncation is None and raw.padding is None:
+            return lambda texts: [e.ids for e in raw.encode_batch(texts, add_special_tokens=True)]
+        return lambda texts: hf(texts, add_special_tokens=True)["input_ids"]
 
     @classmethod
     def from_pretrained(cls, path: str, tokenizer=None, max_length: int = 2048, **kw):
@@ -366,22 +398,45 @@ class B200AuxModel:
             from transformers import AutoTokenizer
             hf = AutoTokenizer.from_pretrained(tokenizer or path)
             tokenizer = lambda text: hf.encode(text)
-            if getattr(hf, "is_fast", False):
-                # same ids as encode() one by one (tokenizer.encode == tokenizer(text).input_ids),
-                # tokenised in parallel by the Rust backend
-                batch = lambda texts: hf(texts, add_special_tokens=True)["input_ids"]
+            batch = cls._batch_encoder(hf)
         return cls(pred, tokenizer, max_length, batch)
+
+    def _encode(self, texts: List[str]) -> List[List[int]]:
+        L = self.max_length
+        if self.batch_tokenizer is not None and len(texts) > 1:
+            ids = self.batch_tokenizer(texts)
+        else:
+            ids = [self.tokenizer(t) for t in texts]
+        return [(p if isinstance(p, list) else list(p)) if len(p) <= L else list(p[:L])
+                for p in ids]
 
     def obtain_aux_scores(self, seq_groups) -> List[float]:
         texts = []
         for sg in seq_groups:
             assert sg.need_aux_model_score()
             texts.append(sg.seqs_dict[next(iter(sg.seqs_dict))].prompt)
-        if self.batch_tokenizer is not None and len(texts) > 1:
-            prompts = [list(p)[:self.max_length] for p in self.batch_tokenizer(texts)]
+        if not texts:
+            return []
+        step = self.chunk_prompts
+        chunks = [texts[c:c + step] for c in range(0, len(texts), step)]
+        parts = []
+        if len(chunks) == 1:
+            parts.append(self.predictor.score_column(self._encode(chunks[0])))
         else:
-            prompts = [list(self.tokenizer(t))[:self.max_length] for t in texts]
-        scores = self.predictor.scores(prompts)
+            # chunk k+1 is tokenised by a helper thread (the Rust tokenizer releases the GIL)
+            # while this thread packs and enqueues the forwards of chunk k; every CUDA call stays
+            # on this thread.  Nothing below waits for the device except the staging ring.
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=1,
+                                                thread_name_prefix="vltr-aux-tokenize")
+            pending = self._pool.submit(self._encode, chunks[0])
+            for k in range(len(chunks)):
+                prompts = pending.result()
+                if k + 1 < len(chunks):
+                    pending = self._pool.submit(self._encode, chunks[k + 1])
+                parts.append(self.predictor.score_column(prompts))
+        scores = (parts[0] if len(parts) == 1 else torch.cat(parts)).tolist()
         for sg, s in zip(seq_groups, scores):
             sg.set_aux_model_score(s)
         return scores

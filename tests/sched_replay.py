@@ -92,15 +92,18 @@ def make_population(n, seed, max_prompt=96, max_out=48):
 
 
 def run(n, seed, schedule_type, num_gpu_blocks, num_cpu_blocks, block_size=4, max_tokens=64,
-        max_seqs=16, use_plugin=False, ranker=None, max_ticks=5000):
-    """Returns the list of per-tick records."""
+        max_seqs=16, use_plugin=False, ranker=None, max_ticks=5000, aborts=None,
+        max_prompt=96, on_tick=None):
+    """Returns the list of per-tick records.  `aborts` maps a tick number to the request ids
+    aborted (Scheduler.abort_seq_group, scheduler.py:379-413) before that tick's schedule();
+    `on_tick(sched, groups, tick)` runs after every simulated engine step."""
     import_reference()
     from vllm import SamplingParams
     from vllm.config import CacheConfig, SchedulerConfig
     from vllm.core.scheduler import Scheduler
     from vllm.sequence import Logprob, Sequence, SequenceGroup, SequenceStatus
 
-    prompt, out_len, score, arrival = make_population(n, seed)
+    prompt, out_len, score, arrival = make_population(n, seed, max_prompt=max_prompt)
     sc = SchedulerConfig(max_tokens, max_seqs, 4096, enable_chunked_prefill=True,
                          schedule_type=schedule_type)
     cc = CacheConfig(block_size, 1.0, 1, "auto")
@@ -123,6 +126,8 @@ def run(n, seed, schedule_type, num_gpu_blocks, num_cpu_blocks, block_size=4, ma
         while nxt < n and arrival[nxt] <= tick:
             sched.add_seq_group(groups[nxt])
             nxt += 1
+        if aborts and tick in aborts:
+            sched.abort_seq_group([str(i) for i in aborts[tick]])
         if not sched.has_unfinished_seqs():
             if nxt >= n:
                 break
@@ -174,5 +179,7 @@ def run(n, seed, schedule_type, num_gpu_blocks, num_cpu_blocks, block_size=4, ma
                         seq.status = SequenceStatus.FINISHED_LENGTH_CAPPED
                         sched.free_seq(seq)
         sched.free_finished_seq_groups()
+        if on_tick is not None:
+            on_tick(sched, groups, tick)
         tick += 1
     return records

@@ -44,6 +44,89 @@ def test_tick_by_tick_parity(n, seed, stype, gpu, cpu, mt, ms):
         assert any(s[3] == -1 for r in ref for s in r["state"]), "no request was ever promoted"
 
 
+def _same(ref, ours):
+    assert len(ours) == len(ref) and len(ref) > 5
+    for t, (a, b) in enumerate(zip(ref, ours)):
+        for key in a:
+            assert a[key] == b[key], f"tick {t}: {key} differs"
+
+
+@pytest.mark.parametrize("stype", ["opt-xxx", "opt-xxx-starv6-period3"])
+def test_parity_with_aborts(stype):
+    """Requests aborted between ticks - from the middle of the waiting queue, from the running and
+    the swapped queue, and ids that are not queued at all: the scores the plugin keeps for the
+    waiting queue must be dropped and rebuilt, tick for tick like the reference."""
+    aborts = {3: [30, 31, 70], 4: [119], 9: [0, 1, 2, 3, 4, 5], 10: [55], 11: [56, 57, 999],
+              20: list(range(60, 100)), 26: [10, 11, 12]}
+    kw = dict(max_tokens=64, max_seqs=16, aborts=aborts)
+    ref = R.run(120, 11, stype, 160, 4096, use_plugin=False, **kw)
+    ours = R.run(120, 11, stype, 160, 4096, use_plugin=True, ranker=R.PythonRanker(), **kw)
+    _same(ref, ours)
+    assert any(r["swap_out"] for r in ref)
+
+
+def test_parity_when_many_waiting_requests_are_admitted_at_once(monkeypatch):
+    """More waiting requests admitted in one tick than are deleted from the queue one by one: the
+    queue (and the scores kept for it) is rebuilt instead."""
+    from vllm_ltr_b200 import ltr_scheduler
+    monkeypatch.setattr(ltr_scheduler, "_EDIT_IN_PLACE_MAX", 3)
+    kw = dict(max_tokens=4096, max_seqs=256, max_prompt=12)
+    ref = R.run(400, 13, "opt-xxx", 4096, 4096, use_plugin=False, **kw)
+    ours = R.run(400, 13, "opt-xxx", 4096, 4096, use_plugin=True, ranker=R.NumpyRanker(), **kw)
+    _same(ref, ours)
+    assert max(r["n_prefill"] for r in ref) > 3
+
+
+def test_parity_with_a_foreign_order():
+    """Somebody else's ``_get_ordered_requests`` bound on the scheduler (here: the reference's own
+    method): the tick takes whatever list it returns."""
+    import types
+
+    def run(plugin):
+        hooked = []
+
+        def on_tick(sched, groups, tick):
+            if plugin and not hooked:
+                from vllm.core.scheduler import Scheduler
+                sched._get_ordered_requests = types.MethodType(
+                    Scheduler._get_opt_ordered_requests, sched)
+                hooked.append(1)
+        return R.run(120, 3, "opt-xxx", 160, 4096, max_tokens=64, max_seqs=16, use_plugin=plugin,
+                     ranker=R.PythonRanker(), on_tick=on_tick)
+    _same(run(False), run(True))
+
+
+def test_idle_counter_reads_like_the_eager_one():
+    """Without starvation control the plugin counts ``idle`` by a per-scheduler tick clock while a
+    request is queued; reads and writes behave like the plain attribute, and a request that left
+    the scheduler (finished or aborted) is a plain ``SequenceGroup`` again."""
+    R.import_reference()
+    from vllm.sequence import SequenceGroup
+    seen = {"queued": 0, "left": 0}
+
+    def on_tick(sched, groups, tick):
+        live = {id(g) for q in (sched.waiting, sched.running, sched.swapped) for g in q}
+        for g in groups:
+            if id(g) in live:
+                assert type(g) is not SequenceGroup and isinstance(g, SequenceGroup)
+                assert "idle" not in g.__dict__
+                before = g.idle
+                g.idle += 0                      # read-modify-write through the property
+                assert g.idle == before
+                seen["queued"] += 1
+            elif hasattr(g, "pri"):              # was added, has left
+                assert type(g) is SequenceGroup
+                assert isinstance(g.__dict__["idle"], int)
+                assert not any(k.startswith("_vltr") for k in g.__dict__)
+                seen["left"] += 1
+    aborts = {5: [7, 8], 12: [20]}
+    ref = R.run(80, 21, "opt-xxx", 160, 4096, max_tokens=64, max_seqs=16, aborts=aborts)
+    ours = R.run(80, 21, "opt-xxx", 160, 4096, max_tokens=64, max_seqs=16, aborts=aborts,
+                 use_plugin=True, ranker=R.PythonRanker(), on_tick=on_tick)
+    _same(ref, ours)
+    assert seen["queued"] > 100 and seen["left"] > 100
+
+
 def test_synthetic_bound_termination():
     """schedule_type "...synthetic((lo,hi,count),)" stops the run after `count` completions
     (scheduler.py:276-282,1697-1721) - handled by the reference's free_finished_seq_groups, which

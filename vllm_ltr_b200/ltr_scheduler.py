@@ -11,13 +11,22 @@ against ``/root/reference/vllm/core/scheduler.py``), but
 
 * the queue sort runs on the GPU (``vltr_ltr_rank_host``, csrc/ltr_rank.cu) instead of Python's
   ``sorted`` over key tuples, and
-* the bookkeeping around it is linear in the number of live requests with a small constant: the
-  reference scans deques for membership (``x in deque``, :1139/:1166/:1187), removes the selected
-  requests one ``list.remove`` at a time (:1213-1214) and tests every live request against the
-  list of scheduled ones (:1358-1365) - about 100-140 ms per tick at 10 000 live requests.  Here
-  only running / swapped requests (hundreds) are looked up by identity, the queue a rank came
-  from is a range test on the rank permutation, the selected requests are a prefix of the order,
-  and the waiting queue is rebuilt with one C-level ``compress``.
+* the bookkeeping around it does not grow with the number of queued requests: the reference
+  scans deques for membership (``x in deque``, :1139/:1166/:1187), removes the selected requests
+  one ``list.remove`` at a time (:1213-1214), tests every live request against the list of
+  scheduled ones (:1358-1365) and rebuilds three lists of all live requests per tick - about
+  100-140 ms per tick at 10 000 live requests.  Here
+  - the scores of the waiting queue (which never change once set) are carried from tick to tick
+    as the float64 array the rank kernel reads: arrivals appended, admitted positions deleted
+    (``_WaitingScores``; re-read from the requests whenever anything else touched the queue);
+  - the ordered list of all live requests is never materialised: the tick walks the rank
+    permutation, which queue a rank came from is a range test on its index, the admitted requests
+    are a prefix of it and the eviction / swap-in candidates are masks over the rest;
+  - the admitted waiting requests are deleted from the deque at their known positions;
+  - without starvation control, ``idle += 1`` on every live request (:1365) is one increment of
+    a tick clock that ``request.idle`` is read against (``_counting_class``).
+  What remains per tick is the work on the <= max_num_seqs requests that actually run (the
+  reference's own block-manager and budget calls) plus the rank kernel.
 
 Quirks of the reference that are part of its observable behaviour and therefore kept:
 * ties in (pri, -score) keep waiting -> running -> swapped deque order (stable sort);
@@ -30,7 +39,7 @@ import os
 import time
 import types
 from collections import deque
-from itertools import compress, islice
+from itertools import chain, compress, islice
 from operator import itemgetter
 from typing import Dict, Iterable, List, Optional
 
@@ -39,6 +48,7 @@ import numpy as np
 from ._lib import check, lib
 
 _WAITING, _RUNNING, _SWAPPED = 0, 1, 2
+_EDIT_IN_PLACE_MAX = 64      # admitted waiting requests deleted from the queue one by one up to here
 
 
 class GpuRanker:
@@ -74,51 +84,230 @@ def _ref():
 
 
 # ---------------------------------------------------------------------------------------------
+# `SequenceGroup.idle` without a pass over every live request per tick
+# ---------------------------------------------------------------------------------------------
+class _TickClock:
+    """Number of ticks this scheduler has run."""
+    __slots__ = ("now",)
+
+    def __init__(self):
+        self.now = 0
+
+
+_COUNTING: Dict[type, type] = {}
+
+
+def _counting_class(base: type) -> type:
+    """Subclass of the reference's ``SequenceGroup`` whose ``idle`` is computed on read.
+
+    scheduler.py:1358-1365 ends every tick with ``idle += 1`` on every live request that did not
+    run - at 10 000 queued requests that is 10 000 scattered attribute updates (cache misses on
+    10 000 instance dicts) per engine step, for a counter nothing reads unless starvation
+    control is on.  While a request is queued in a scheduler ticked by this plugin WITHOUT
+    starvation control its class is this subclass: ``idle`` reads as
+    ``value when last set + ticks since`` and the tick advances one clock instead.  Reads and
+    writes of ``request.idle`` give exactly what the reference's eager counter would hold; when
+    the request leaves the scheduler (finished, aborted, run cut off by the synthetic bound) it
+    is turned back into a plain ``SequenceGroup`` with a plain ``idle`` attribute."""
+    cls = _COUNTING.get(base)
+    if cls is None:
+        def _get(self):
+            d = self.__dict__
+            return d["_vltr_idle"] + d["_vltr_clock"].now - d["_vltr_since"]
+
+        def _set(self, value):
+            d = self.__dict__
+            d["_vltr_idle"] = value
+            d["_vltr_since"] = d["_vltr_clock"].now
+
+        cls = type("TickCounted" + base.__name__, (base,),
+                   {"__slots__": (), "idle": property(_get, _set), "__module__": __name__,
+                    "__doc__": _counting_class.__doc__})
+        globals()[cls.__name__] = cls              # importable by name (pickle)
+        _COUNTING[base] = cls
+    return cls
+
+
+def _count_by_clock(req, clock: _TickClock) -> None:
+    base = type(req)
+    if base in _COUNTING.values():
+        return
+    d = req.__dict__
+    d["_vltr_idle"] = d.pop("idle", 0)
+    d["_vltr_since"] = clock.now
+    d["_vltr_clock"] = clock
+    req.__class__ = _counting_class(base)
+
+
+def _count_eagerly(req) -> None:
+    cls = type(req)
+    if cls not in _COUNTING.values():
+        return
+    value = req.idle
+    req.__class__ = cls.__mro__[1]
+    d = req.__dict__
+    del d["_vltr_idle"], d["_vltr_since"], d["_vltr_clock"]
+    d["idle"] = value
+
+
+def free_finished_seq_groups(self) -> None:
+    """The reference's method (scheduler.py:1697-1723), then: requests that left the queues get
+    their plain ``idle`` attribute back."""
+    running, waiting, swapped = self.running, self.waiting, self.swapped
+    n = len(running)
+    self._vltr_ref_free_finished()
+    if self.running is not running and len(self.running) != n:
+        kept = set(map(id, self.running))
+        for r in running:
+            if id(r) not in kept:
+                _count_eagerly(r)
+    # the synthetic / time bound was reached: every queue replaced by an empty one
+    if self.waiting is not waiting:
+        for r in waiting:
+            _count_eagerly(r)
+    if self.swapped is not swapped:
+        for r in swapped:
+            _count_eagerly(r)
+
+
+def abort_seq_group(self, request_id) -> None:
+    """The reference's method (scheduler.py:379-413); the aborted requests get their plain
+    ``idle`` attribute back first."""
+    ids = {request_id} if isinstance(request_id, str) else set(request_id)
+    for q in (self.waiting, self.running, self.swapped):
+        for r in q:
+            if r.request_id in ids:
+                _count_eagerly(r)
+    return self._vltr_ref_abort(ids)
+
+
+# ---------------------------------------------------------------------------------------------
 # _get_ordered_requests for schedule_type "opt*"        (scheduler.py:969-1000)
 # ---------------------------------------------------------------------------------------------
-def get_opt_ordered_requests(self) -> list:
-    # need_aux_model_score() is `aux_model_score is None` (vllm/sequence.py:460-461): read the
-    # attribute directly.  One pass gathers the waiting queue's scores (the sort needs them
-    # anyway); the list of unscored requests is only built on the ticks that have any.
-    live = list(self.waiting)
-    nw = len(live)
-    scores = [r.aux_model_score for r in live]
+class _WaitingScores:
+    """Scores of the waiting queue kept between ticks (starvation control off).
+
+    A waiting request's score never changes once the predictor has set it, and the reference
+    only ever appends to the waiting queue (``add_seq_group``), removes from it
+    (``abort_seq_group``) or - this tick itself - takes the admitted requests out.  So the float64
+    array the rank kernel reads is carried over from tick to tick: new arrivals are appended, the
+    admitted positions deleted, and no pass over the ~10^4 queued requests is needed to rebuild
+    it.  ``valid_for`` is the check that nothing else touched the queue: same deque object, not
+    shorter, and the first and last request of the remembered content still sit at index 0 and
+    n-1 (any ``remove`` at or before n-1 shifts the last one to n-2)."""
+    __slots__ = ("queue", "reqs", "scores")
+
+    def __init__(self, queue, reqs, scores):
+        self.queue, self.reqs, self.scores = queue, reqs, scores
+
+    def valid_for(self, queue) -> bool:
+        n = len(self.reqs)
+        return (queue is self.queue and len(queue) >= n
+                and (n == 0 or (queue[0] is self.reqs[0] and queue[n - 1] is self.reqs[-1])))
+
+
+def _scores_of_waiting(self, reqs: list) -> list:
+    """aux_model_score of every request of `reqs`, after sending the unscored ones to the
+    predictor in queue order (scheduler.py:971-982).  need_aux_model_score() is
+    `aux_model_score is None` (vllm/sequence.py:460-461): the attribute is read directly."""
+    scores = [r.aux_model_score for r in reqs]
     if None in scores:
-        unscored = [r for r, sc in zip(live, scores) if sc is None]
+        unscored = [r for r, sc in zip(reqs, scores) if sc is None]
         timed = int(os.environ.get("OPT_TIME", 0))
         t0 = time.time() if timed else 0.0
         self.aux_model.obtain_aux_scores(unscored)
         if timed:
             print("OPT-TIME: ", time.time() - t0)
-        scores = [r.aux_model_score for r in live]
-    live.extend(self.running)
-    nr = len(live) - nw
-    live.extend(self.swapped)
-    scores.extend([r.aux_model_score for r in islice(live, nw, None)])
+        scores = [r.aux_model_score for r in reqs]
+    return scores
+
+
+def _rank_live(self):
+    """One ranking of the live requests.  Returns ``(wreqs, others, order, nw, nr)``:
+    live = wreqs (the waiting queue, a list) ++ others (running ++ swapped), `order` the
+    permutation of range(len(live)) in schedule order (int32), nw / nr the number of waiting /
+    running requests.  Which queue a rank came from is a range test on `order`."""
+    w = self.waiting
+    nw = len(w)
+    keep = self.starv == -1
+    cache = getattr(self, "_vltr_wcache", None) if keep else None
+    clock = self._vltr_clock
+    if cache is not None and cache.valid_for(w):
+        wreqs, wscores = cache.reqs, cache.scores
+        n0 = len(wreqs)
+        if nw > n0:                                      # arrivals since the last tick
+            tail = [w[i] for i in range(n0 - nw, 0)]
+            ts = np.asarray(_scores_of_waiting(self, tail), dtype=np.float64)
+            wreqs.extend(tail)
+            cache.scores = wscores = np.concatenate((wscores, ts))
+            if clock is not None:
+                for r in tail:
+                    _count_by_clock(r, clock)
+    else:
+        wreqs = list(w)
+        wscores = np.asarray(_scores_of_waiting(self, wreqs), dtype=np.float64)
+        self._vltr_wcache = _WaitingScores(w, wreqs, wscores) if keep else None
+        if clock is not None:
+            for r in wreqs:
+                _count_by_clock(r, clock)
+    others = list(self.running)
+    nr = len(others)
+    others.extend(self.swapped)
     pri = None
-    if self.starv != -1:
+    if not keep:
         # starvation control: a request idle for `starv` ticks is promoted for `period`
         # scheduled steps, then demoted again
-        for r in live:
+        for r in chain(wreqs, others):
             if r.idle >= self.starv:
                 r.pri, r.idle, r.runs = -1, 0, self.period
             elif r.pri == -1 and r.runs <= 0:
                 r.pri = 0
-        pri = [r.pri for r in live]
-    order = self._vltr_ranker.order(scores, pri, negate=True)
-    n = len(live)
-    if n >= 2:
-        ordered = list(itemgetter(*order.tolist())(live))
+        pri = [r.pri for r in chain(wreqs, others)]
+    if others:
+        scores = np.concatenate(
+            (wscores, np.asarray([r.aux_model_score for r in others], dtype=np.float64)))
     else:
-        ordered = list(live)
-    # remembered for general_schedule: which queue every rank came from is a range test on the
-    # permutation (live = waiting ++ running ++ swapped), no per-request lookups
-    self._vltr_tick = (ordered, live, order, nw, nr)
-    return ordered
+        scores = wscores
+    order = self._vltr_ranker.order(scores, pri, negate=True)
+    return wreqs, others, order, nw, nr
+
+
+def get_opt_ordered_requests(self) -> list:
+    """The reference's return value: every live request, best rank first.  (The tick below does
+    not materialise this list - it walks the permutation.)"""
+    wreqs, others, order, _, _ = _rank_live(self)
+    live = wreqs + others
+    if len(live) >= 2:
+        return list(itemgetter(*order.tolist())(live))
+    return live
 
 
 def update_opt_priority(self) -> None:     # scheduler.py:1002-1003
     return None
+
+
+def _foreign_order(self, ordered: list):
+    """An order produced by somebody else's ``_get_ordered_requests``: expressed as the same
+    ``(wreqs, others, order, nw, nr)`` by looking every request up by identity."""
+    wreqs = list(self.waiting)
+    others = list(self.running)
+    nw, nr = len(wreqs), len(others)
+    others.extend(self.swapped)
+    pos = {id(r): i for i, r in enumerate(chain(wreqs, others))}
+    try:
+        order = np.fromiter((pos[id(r)] for r in ordered), dtype=np.int32, count=len(ordered))
+    except KeyError:
+        raise AssertionError("seqgroup not in all lists") from None    # scheduler.py:1211
+    self._vltr_wcache = None
+    if self._vltr_clock is not None:
+        for r in chain(wreqs, others):
+            _count_by_clock(r, self._vltr_clock)
+    return wreqs, others, order, nw, nr
+
+
+def _iter_ranks(order: np.ndarray, block: int = 512):
+    for s in range(0, len(order), block):
+        yield from order[s:s + block].tolist()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -222,40 +411,53 @@ def _reserve_free_blocks(self, S, blocks_needed: int, pinned: list,
 # _schedule for the rank-ordered policies                (scheduler.py:1101-1373)
 # ---------------------------------------------------------------------------------------------
 def general_schedule(self):
+    try:
+        return _tick(self)
+    except BaseException:
+        self._vltr_wcache = None          # whatever state the queues are left in is re-read
+        raise
+
+
+def _tick(self):
     S = _ref()
     WAITING, RUNNING, SWAPPED = (S.SequenceStatus.WAITING, S.SequenceStatus.RUNNING,
                                  S.SequenceStatus.SWAPPED)
     self._update_priority()
-    ordered = self._get_ordered_requests()
-    live_before = len(self.waiting) + len(self.running) + len(self.swapped)
+    if getattr(self._get_ordered_requests, "__func__", None) is get_opt_ordered_requests:
+        wreqs, others, order, nw, nr = _rank_live(self)
+    else:
+        wreqs, others, order, nw, nr = _foreign_order(self, self._get_ordered_requests())
+    nwr = nw + nr
+    live_before = nw + len(others)
     cfg = self.scheduler_config
     budget = S.SchedulingBudget(token_budget=cfg.max_num_batched_tokens,
                                 max_num_seqs=cfg.max_num_seqs)
     final_budget = S.SchedulingBudget(token_budget=cfg.max_num_batched_tokens,
                                       max_num_seqs=cfg.max_num_seqs)
-    # which queue a request sits in.  Running and swapped requests (at most max_num_seqs plus
-    # whatever was preempted - hundreds) are looked up by identity; everything else in the order
-    # is a waiting request.  When the order came from get_opt_ordered_requests the ranks of the
-    # running / swapped requests are also known from the permutation itself (range tests on the
-    # indices into waiting ++ running ++ swapped), so no pass over the ~10^4 waiting requests is
-    # needed anywhere below.
-    tick = getattr(self, "_vltr_tick", None)
-    fast = tick is not None and tick[0] is ordered and len(ordered) == live_before
-    where: Dict[int, int] = {id(r): _RUNNING for r in self.running}
-    for r in self.swapped:
+    # which queue a request sits in: a range test on its index into wreqs ++ running ++ swapped
+    # while the ranks are walked; afterwards running and swapped requests (at most max_num_seqs
+    # plus whatever was preempted - hundreds) are looked up by identity and everything else is a
+    # waiting request.  No pass over the ~10^4 waiting requests is needed anywhere below.
+    where: Dict[int, int] = {id(r): _RUNNING for r in islice(others, nr)}
+    for r in islice(others, nr, None):
         where[id(r)] = _SWAPPED
-    if not fast:
-        for r in self.waiting:
-            where[id(r)] = _WAITING
-    default_tag = _WAITING if fast else None
 
     # ---- admit in rank order until a budget runs out: the selection is a prefix of the order
     bm = self.block_manager
     blocks_needed = 0
-    k = 0
-    for req in ordered:
-        tag = where.get(id(req), default_tag)
-        if tag == _RUNNING:
+    selected, selected_at = [], []
+    for idx in _iter_ranks(order):
+        if idx < nw:
+            req = wreqs[idx]
+            new_tokens = self._get_num_new_tokens(req, WAITING, True, budget)
+            assert new_tokens <= self.prompt_limit, "req exceed prompt limit"
+            new_seqs = req.get_max_num_running_seqs()
+            if new_tokens == 0 or not budget.can_schedule(num_new_tokens=new_tokens,
+                                                          num_new_seqs=new_seqs):
+                break
+            blocks = len(req.get_seqs()[0].logical_token_blocks)
+        elif idx < nwr:
+            req = others[idx - nw]
             new_tokens = self._get_num_new_tokens(req, RUNNING, True, budget)
             if new_tokens == 0:
                 assert budget.remaining_token_budget() == 0
@@ -264,7 +466,8 @@ def general_schedule(self):
             if not budget.can_schedule(num_new_tokens=new_tokens, num_new_seqs=new_seqs):
                 break
             blocks = new_seqs
-        elif tag == _SWAPPED:
+        else:
+            req = others[idx - nw]
             new_seqs = req.get_max_num_running_seqs()
             new_tokens = self._get_num_new_tokens(req, SWAPPED, True, budget)
             n_swapped = req.num_seqs(status=SWAPPED)
@@ -272,33 +475,19 @@ def general_schedule(self):
                                                           num_new_seqs=new_seqs):
                 break
             blocks = len(bm._get_physical_blocks(req)) + n_swapped
-        elif tag == _WAITING:
-            new_tokens = self._get_num_new_tokens(req, WAITING, True, budget)
-            assert new_tokens <= self.prompt_limit, "req exceed prompt limit"
-            new_seqs = req.get_max_num_running_seqs()
-            if new_tokens == 0 or not budget.can_schedule(num_new_tokens=new_tokens,
-                                                          num_new_seqs=new_seqs):
-                break
-            blocks = len(req.get_seqs()[0].logical_token_blocks)
-        else:
-            raise AssertionError("seqgroup not in all lists")
         budget.add_num_batched_tokens(req.request_id, new_tokens)
         budget.add_num_seqs(req.request_id, new_seqs)
         req.num_new_tokens, req.num_new_seqs = new_tokens, new_seqs
         blocks_needed += blocks
-        k += 1
-    selected = ordered[:k]
-    if fast:
-        _, live, order, nw, nr = tick
-        tail = order[k:]
-        run_ranks = np.flatnonzero((tail >= nw) & (tail < nw + nr))
-        swp_ranks = np.flatnonzero(tail >= nw + nr)
-        evict_candidates = (ordered[k + i] for i in run_ranks[::-1].tolist())
-        swapin_candidates = (ordered[k + i] for i in swp_ranks.tolist())
-    else:
-        rest = ordered[k:]
-        evict_candidates = (r for r in reversed(rest) if where.get(id(r)) == _RUNNING)
-        swapin_candidates = (r for r in rest if where.get(id(r)) == _SWAPPED)
+        selected.append(req)
+        selected_at.append(idx)
+    # the unselected members of the running queue (lowest rank first) and of the swapped queue
+    # (best rank first): range tests on the rest of the permutation
+    tail = order[len(selected):]
+    evict_at = tail[(tail >= nw) & (tail < nwr)][::-1].tolist()
+    swapin_at = tail[tail >= nwr].tolist()
+    evict_candidates = (others[i - nw] for i in evict_at)
+    swapin_candidates = (others[i - nw] for i in swapin_at)
 
     dropped_running: set = set()      # ids leaving self.running by preemption
     execute, preempted, swapped_out, to_swap_out, to_swap_in = _reserve_free_blocks(
@@ -311,7 +500,7 @@ def general_schedule(self):
     taken = {_WAITING: set(), _RUNNING: set(), _SWAPPED: set()}
     SSG = S.ScheduledSequenceGroup
     for req in execute:
-        tag = where.get(id(req), default_tag)
+        tag = where.get(id(req), _WAITING)
         if tag == _RUNNING and id(req) in dropped_running:
             tag = None
         if tag is None or id(req) in taken[tag]:
@@ -340,24 +529,36 @@ def general_schedule(self):
     assert final_budget.num_batched_tokens <= cfg.max_num_batched_tokens
     assert budget.num_curr_seqs <= cfg.max_num_seqs
 
-    # ---- rebuild the three queues in one pass each ----------------------------------------------
+    # ---- the three queues after the tick -----------------------------------------------------------
     gone_w, gone_r, gone_s = taken[_WAITING], taken[_RUNNING] | dropped_running, taken[_SWAPPED]
-    if not gone_w:
-        waiting = deque(self.waiting)
-    elif fast:
-        # the admitted waiting requests sit at known positions of the old queue: order[rank]
-        keep = bytearray(b"\x01") * nw
-        for rank, req in enumerate(selected):
-            if id(req) in gone_w:
-                keep[order[rank]] = 0
-        waiting = deque(compress(islice(live, nw), keep))
-    else:
-        waiting = deque(r for r in self.waiting if id(r) not in gone_w)
-    waiting.extendleft(preempted)
-    running = deque(r for r in self.running if id(r) not in gone_r)
+    waiting = self.waiting
+    if gone_w:
+        # the admitted waiting requests sit at known positions of the queue: their indices
+        at = sorted((i for i, r in zip(selected_at, selected) if i < nw and id(r) in gone_w),
+                    reverse=True)
+        cache = getattr(self, "_vltr_wcache", None)
+        if len(at) <= _EDIT_IN_PLACE_MAX:
+            for i in at:                       # a handful per tick: deleted in place
+                del waiting[i]
+                del wreqs[i]
+            if cache is not None:
+                cache.scores = np.delete(cache.scores, at)
+        else:
+            keep = bytearray(b"\x01") * nw
+            for i in at:
+                keep[i] = 0
+            wreqs = list(compress(wreqs, keep))
+            waiting = deque(wreqs)
+            if cache is not None:
+                self._vltr_wcache = _WaitingScores(
+                    waiting, wreqs, cache.scores[np.frombuffer(keep, dtype=np.bool_)])
+    if preempted:
+        waiting.extendleft(preempted)
+        self._vltr_wcache = None
+    running = deque(r for r in islice(others, nr) if id(r) not in gone_r)
     for group in (new_prefill, run_decode, run_prefill, swp_decode, swp_prefill):
         running.extend(s.seq_group for s in group)
-    swapped = deque(r for r in self.swapped if id(r) not in gone_s)
+    swapped = deque(r for r in islice(others, nr, None) if id(r) not in gone_s)
     swapped.extend(swapped_out)
     self.waiting, self.running, self.swapped = waiting, running, swapped
     assert len(waiting) + len(running) + len(swapped) == live_before
@@ -378,9 +579,13 @@ def general_schedule(self):
     # ---- idle / runs bookkeeping for every live request ----------------------------------------
     # (scheduler.py:1358-1365: a request that ran has idle = 0 and, while promoted, one run less;
     # every other live request has been idle one tick more)
-    for q in (swapped, running, waiting):
-        for r in q:
-            r.idle += 1
+    clock = self._vltr_clock
+    if clock is not None:
+        clock.now += 1                    # every live request: one tick more (read on demand)
+    else:
+        for q in (swapped, running, waiting):
+            for r in q:
+                r.idle += 1
     for sg in out.scheduled_seq_groups:
         r = sg.seq_group
         if r.pri == -1:
@@ -444,6 +649,18 @@ def install(scheduler, ranker=None):
     if not st.startswith("opt"):
         raise ValueError(f"vllm_ltr_b200 LTR tick handles schedule_type 'opt*', got {st!r}")
     scheduler._vltr_ranker = GpuRanker() if ranker is None else ranker
+    scheduler._vltr_wcache = None
+    # starvation control reads every request's idle count every tick: counted eagerly, as the
+    # reference does; otherwise by the tick clock (see _counting_class)
+    scheduler._vltr_clock = _TickClock() if scheduler.starv == -1 else None
+    if scheduler._vltr_clock is not None:
+        for r in chain(scheduler.waiting, scheduler.running, scheduler.swapped):
+            _count_by_clock(r, scheduler._vltr_clock)
+        if not hasattr(scheduler, "_vltr_ref_free_finished"):
+            scheduler._vltr_ref_free_finished = scheduler.free_finished_seq_groups
+            scheduler._vltr_ref_abort = scheduler.abort_seq_group
+        scheduler.free_finished_seq_groups = types.MethodType(free_finished_seq_groups, scheduler)
+        scheduler.abort_seq_group = types.MethodType(abort_seq_group, scheduler)
     scheduler._schedule = types.MethodType(general_schedule, scheduler)
     scheduler._get_ordered_requests = types.MethodType(get_opt_ordered_requests, scheduler)
     scheduler._update_priority = types.MethodType(update_opt_priority, scheduler)

@@ -31,6 +31,10 @@ Contexts are the running contexts of a synthetic ShareGPT-shaped trace (BASELINE
             and stock scheduler / predictor engine and once with vllm_ltr_b200.install() +
             install_engine(); output tokens/s and p50 request latency of both
             (tools/engine_trace.py, one subprocess per arm)
+  trace_poisson  (N=1) the same two engines with the trace's requests ARRIVING over time
+            (Gamma(cv=1) gaps at --trace-poisson-rate requests/s for --trace-poisson-time s,
+            benchmark_serving_real.py:159-176 / bench-lmsys.sh), schedule "opt-xxx", every
+            request run to its end; output tokens/s and p50 latency from arrival
 
 N > 1 (torchrun): tensor-parallel shards of the same model (q/kv heads and MLP width divided,
 two exchanges of [B, hidden] per layer, fused with the residual add + RMSNorm that follows),
@@ -451,12 +455,21 @@ def step_pair(name, batch, steps, dev, ref, peak, clocks, ours=True, layers=None
     return res
 
 
-def run_trace_arm(arm, args, clocks, timeout_s):
-    """One arm of the engine-level trace in its own process (vllm._C is bound per process)."""
+def run_trace_arm(arm, args, clocks, timeout_s, poisson=False):
+    """One arm of the engine-level trace in its own process (vllm._C is bound per process).
+    `poisson`: requests arrive at --trace-poisson-rate for --trace-poisson-time seconds and every
+    one runs to its end (no synthetic stop rule); otherwise all requests are queued at t=0."""
     out = os.path.join("/tmp", f"vltr_trace_{arm}_{os.getpid()}.json")
     cmd = [sys.executable, os.path.join(TOOLS, "engine_trace.py"), "--arm", arm,
-           "--model", args.trace_model, "--num-prompts", str(args.trace_prompts),
-           "--stop-after", str(args.trace_stop), "--json", out]
+           "--model", args.trace_model, "--json", out]
+    if poisson:
+        n = int(args.trace_poisson_rate * args.trace_poisson_time * 1.5) + 16
+        cmd += ["--num-prompts", str(n), "--stop-after", "0",
+                "--request-rate", str(args.trace_poisson_rate),
+                "--request-time", str(args.trace_poisson_time),
+                "--max-output", str(args.trace_poisson_max_output)]
+    else:
+        cmd += ["--num-prompts", str(args.trace_prompts), "--stop-after", str(args.trace_stop)]
     t0 = time.time()
     try:
         r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
@@ -470,10 +483,10 @@ def run_trace_arm(arm, args, clocks, timeout_s):
         d = json.load(f)
     os.unlink(out)
     s = d["summary"]
-    keep = ("tokens_per_s", "p50_latency_s", "p90_latency_s", "requests_per_s", "finished",
-            "generated_tokens", "elapsed_s", "steps", "schedule_s", "execute_model_s",
-            "predictor_s", "other_host_s", "add_requests_s")
-    res = {k: s[k] for k in keep}
+    keep = ("tokens_per_s", "p50_latency_s", "p90_latency_s", "mean_latency_s", "requests_per_s",
+            "num_requests", "finished", "generated_tokens", "elapsed_s", "steps", "schedule_s",
+            "execute_model_s", "predictor_s", "other_host_s", "add_requests_s", "arrivals")
+    res = {k: s[k] for k in keep if k in s}
     res["engine_init_s"] = d["engine"]["init_s"]
     res["num_gpu_blocks"] = d["engine"]["num_gpu_blocks"]
     res["wall_s"] = t1 - t0
@@ -632,6 +645,14 @@ def _main(out):
     ap.add_argument("--trace-model", default="llama-2-7b")
     ap.add_argument("--trace-prompts", type=int, default=10000)
     ap.add_argument("--trace-stop", type=int, default=1000)
+    ap.add_argument("--trace-poisson-rate", type=float, default=32.0,
+                    help="N=1: second engine-level trace with Poisson arrivals at this many "
+                         "requests/s (bench-lmsys.sh / benchmark_serving_real.py:159-176); 0 = off")
+    ap.add_argument("--trace-poisson-time", type=float, default=10.0,
+                    help="seconds of arrivals (the reference scripts: --request-time 60)")
+    ap.add_argument("--trace-poisson-max-output", type=int, default=192,
+                    help="output lengths of the trace clipped to this, so that the leg drains "
+                         "within the bench's time budget")
     ap.add_argument("--extras-budget-s", type=float, default=540.0,
                     help="stop starting secondary measurements once the run is this old")
     args = ap.parse_args()
@@ -1047,6 +1068,27 @@ def _main(out):
                 tr["tokens_per_s_ratio"] = tr["ours"]["tokens_per_s"] / tr["ref_cuda"]["tokens_per_s"]
                 tr["p50_latency_ratio"] = tr["ours"]["p50_latency_s"] / tr["ref_cuda"]["p50_latency_s"]
             line["trace"] = tr
+            if args.trace_poisson_rate > 0:
+                tp = {"workload": f"{args.trace_model} + OPT-125M predictor as in `trace`; "
+                                  f"requests of the synthetic ShareGPT trace arriving with "
+                                  f"Gamma(cv=1) gaps at {args.trace_poisson_rate:g} requests/s for "
+                                  f"{args.trace_poisson_time:g} s (benchmark_serving_real.py:159-176)"
+                                  f", outputs clipped to {args.trace_poisson_max_output} tokens, "
+                                  "schedule \"opt-xxx\", every request run to its end; a request "
+                                  "enters the engine at the first step boundary after its arrival",
+                      "metric": "output tokens/s and p50 request latency from arrival"}
+                for label, arm in arms:
+                    left = budget_left()
+                    if left < 150:
+                        tp[label] = {"skipped": f"time budget ({args.extras_budget_s:.0f} s) spent"}
+                        continue
+                    tp[label] = run_trace_arm(arm, args, clocks2, min(left, 150.0), poisson=True)
+                if "p50_latency_s" in tp.get("ours", {}) and "p50_latency_s" in tp.get("ref_cuda", {}):
+                    tp["tokens_per_s_ratio"] = (tp["ours"]["tokens_per_s"]
+                                                / tp["ref_cuda"]["tokens_per_s"])
+                    tp["p50_latency_ratio"] = (tp["ours"]["p50_latency_s"]
+                                               / tp["ref_cuda"]["p50_latency_s"])
+                line["trace_poisson"] = tp
     clocks2.stop()
     line["bench_wall_s"] = time.time() - t_run0
     emit()

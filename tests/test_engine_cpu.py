@@ -82,3 +82,44 @@ def test_install_engine_reads_the_reference_predictor_config(env, monkeypatch):
     done = integration.install_engine(eng, scheduler=False, prefill=False)
     assert sched.aux_model == "B200AUX" and done["predictor"].startswith("B200AuxModel")
     assert seen == {"path": "/ckpt", "tokenizer": "/tok", "max_length": 1536}
+
+
+def test_trace_with_poisson_arrivals_through_engine(env, monkeypatch):
+    """tools/engine_trace.run_trace with arrival times (the "Poisson" configuration,
+    benchmark_serving_real.py:159-176): requests enter the engine as their arrival time passes,
+    every one of them finishes with all its tokens, and latency counts from the arrival."""
+    import numpy as np
+    E, assets = env
+    n = 120
+    reqs = E.make_trace(n, 32000, 4096, max_output=24)
+    arrivals = E.make_arrivals(n, rate=400.0)
+    assert arrivals[0] == 0.0 and np.all(np.diff(arrivals) >= 0) and 0.1 < arrivals[-1] < 1.0
+    assert abs(np.diff(E.make_arrivals(20000, rate=50.0)).mean() - 1 / 50.0) < 1e-3
+    res = {}
+    for plugin in (False, True):
+        llm = F.build_fake_llm(assets, "opt-xxx", gpu_blocks=600, cpu_blocks=32768)
+        eng = llm.llm_engine
+        eng.scheduler.aux_model = R.StubScorer({})
+        eng.scheduler.aux_model.obtain_aux_scores = lambda sgs: [
+            sg.set_aux_model_score(0.0) for sg in sgs]
+        if plugin:
+            from vllm_ltr_b200 import integration, ltr_scheduler
+            monkeypatch.setattr(ltr_scheduler, "GpuRanker", lambda: R.NumpyRanker())
+            integration.install_engine(eng, predictor=False, prefill=False)
+        seen_live = []
+        inner = eng.scheduler.schedule
+
+        def spy(inner=inner, eng=eng):
+            seen_live.append(eng.scheduler.get_num_unfinished_seq_groups())
+            return inner()
+        eng.scheduler.schedule = spy
+        out = E.run_trace(llm, reqs, scores="synthetic", arrivals=arrivals)["summary"]
+        res[plugin] = out
+        assert out["finished"] == n and out["generated_tokens"] == sum(r[2] for r in reqs)
+        assert out["arrivals"].startswith(f"{n} requests over")
+        assert out["elapsed_s"] >= arrivals[-1]
+        # latency is measured from each request's own arrival: nothing can take longer than the run
+        assert 0 < out["p50_latency_s"] <= out["p90_latency_s"] <= out["elapsed_s"]
+        # the requests trickled in: the first steps saw only a few of them
+        assert seen_live[0] < n // 2 and max(seen_live) > seen_live[0]
+    assert res[False]["generated_tokens"] == res[True]["generated_tokens"]

@@ -29,7 +29,7 @@ import math
 import os
 import sys
 import time
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -200,6 +200,15 @@ def make_trace(n: int, vocab: int, max_len: int, seed: int = 0, tau: float = 0.5
     return reqs
 
 
+def make_arrivals(n: int, rate: float, cv: float = 1.0, seed: int = 0) -> np.ndarray:
+    """Arrival offsets in seconds of `n` requests sent at `rate` requests/s: the first at t=0, then
+    Gamma(shape=1/cv^2, scale=cv^2/rate) gaps - benchmark_serving_real.py:159-176 (cv=1: Poisson
+    arrivals, the "Poisson" configuration of bench-lmsys.sh)."""
+    rng = np.random.default_rng(seed + 1)
+    gaps = rng.gamma(1.0 / (cv * cv), cv * cv / rate, max(n - 1, 0))
+    return np.concatenate(([0.0], np.cumsum(gaps)))[:n]
+
+
 # --------------------------------------------------------------------------------------------
 # engine construction
 # --------------------------------------------------------------------------------------------
@@ -358,23 +367,37 @@ class TimedScores:
 
 def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = False,
               logprobs: Optional[int] = None, temperature: float = 0.0,
-              max_steps: Optional[int] = None, profile: Optional[tuple] = None) -> dict:
+              max_steps: Optional[int] = None, profile: Optional[tuple] = None,
+              arrivals: Optional[Sequence[float]] = None) -> dict:
     """The request loop of benchmark_throughput_original.py:251-270 + LLM._run_engine
-    (entrypoints/llm.py:221-246), instrumented per step."""
+    (entrypoints/llm.py:221-246), instrumented per step.  With `arrivals` (seconds from the start,
+    ascending, one per request) a request enters the engine at the first step boundary after its
+    arrival time - what the API server's engine loop does with requests that come in while a
+    step runs (async_llm_engine.py:209) - and its latency counts from its arrival."""
     import torch
     from vllm import SamplingParams
     eng = llm.llm_engine
     sched = eng.scheduler
     synth = {}
-    t_add = time.perf_counter()
-    for prompt, _, output_len, score in reqs:
-        sp = SamplingParams(n=1, temperature=temperature, top_p=1.0, use_beam_search=False,
-                            ignore_eos=True, max_tokens=output_len, est_tokens=None,
-                            logprobs=logprobs)
-        rid = str(next(llm.request_counter))
+
+    def params(output_len):
+        return SamplingParams(n=1, temperature=temperature, top_p=1.0, use_beam_search=False,
+                              ignore_eos=True, max_tokens=output_len, est_tokens=None,
+                              logprobs=logprobs)
+
+    t_add = 0.0
+    arrived_at: Dict[str, float] = {}
+    rids = [str(next(llm.request_counter)) for _ in reqs]
+    for rid, (_, _, _, score) in zip(rids, reqs):
         synth[rid] = score
-        eng.add_request(rid, prompt, sp, None)
-    t_add = time.perf_counter() - t_add
+    if arrivals is None:
+        t_add = time.perf_counter()
+        for rid, (prompt, _, output_len, _) in zip(rids, reqs):
+            eng.add_request(rid, prompt, params(output_len), None)
+        t_add = time.perf_counter() - t_add
+    else:
+        assert len(arrivals) == len(reqs)
+        assert all(b >= a for a, b in zip(arrivals, arrivals[1:])), "arrivals must ascend"
     aux = None
     if getattr(sched, "aux_model", None) is not None:
         aux = TimedScores(sched.aux_model, synth if scores == "synthetic" else None)
@@ -411,7 +434,26 @@ def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = Fals
     start = time.perf_counter()
     sched.start_time = time.time()
     prof = None
-    while eng.has_unfinished_requests():
+    nxt = 0
+    n_req = len(reqs)
+    while True:
+        if arrivals is not None and nxt < n_req:
+            now = time.perf_counter() - start
+            if arrivals[nxt] <= now:
+                t = time.perf_counter()
+                while nxt < n_req and arrivals[nxt] <= now:
+                    prompt, _, output_len, _ = reqs[nxt]
+                    eng.add_request(rids[nxt], prompt, params(output_len), None)
+                    arrived_at[rids[nxt]] = float(arrivals[nxt])
+                    nxt += 1
+                t_add += time.perf_counter() - t
+            elif not eng.has_unfinished_requests():
+                time.sleep(min(max(arrivals[nxt] - now, 0.0), 0.05))     # idle until the next arrival
+                continue
+        if not eng.has_unfinished_requests():
+            if arrivals is None or nxt >= n_req:
+                break
+            continue
         if profile is not None and steps == profile[0]:
             from torch.profiler import ProfilerActivity
             from torch.profiler import profile as _profile
@@ -421,7 +463,7 @@ def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = Fals
             prof_t0 = time.perf_counter()
         for out in eng.step():
             if out.finished:
-                out.latency = time.perf_counter() - start
+                out.latency = time.perf_counter() - start - arrived_at.get(out.request_id, 0.0)
                 outputs.append(out)
         steps += 1
         if prof is not None and steps == profile[0] + profile[1]:
@@ -442,6 +484,8 @@ def run_trace(llm, reqs, scores: str = "synthetic", record_schedule: bool = Fals
     lat = [o.latency for o in outputs]
     res = {
         "num_requests": len(reqs), "finished": len(outputs), "generated_tokens": gen,
+        "arrivals": "all at t=0" if arrivals is None else
+                    f"{len(reqs)} requests over {float(arrivals[-1]) if len(reqs) else 0.0:.1f} s",
         "elapsed_s": elapsed, "steps": steps,
         "tokens_per_s": gen / elapsed if elapsed > 0 else 0.0,
         "requests_per_s": len(outputs) / elapsed if elapsed > 0 else 0.0,
@@ -503,6 +547,12 @@ def main():
                     help='N of "opt-xxx-synthetic((-1,-1,N),)"; 0 = run every request to the end')
     ap.add_argument("--max-output", type=int, default=None)
     ap.add_argument("--min-output", type=int, default=None)
+    ap.add_argument("--request-rate", type=float, default=None,
+                    help="requests/s with Gamma(cv) gaps (benchmark_serving_real.py:159-176) instead "
+                         "of every request at t=0")
+    ap.add_argument("--request-time", type=float, default=None,
+                    help="with --request-rate: only the requests arriving within this many seconds")
+    ap.add_argument("--cv", type=float, default=1.0)
     ap.add_argument("--scores", choices=["synthetic", "predictor"], default="synthetic")
     ap.add_argument("--kv-cache-dtype", default="auto")
     ap.add_argument("--gpu-memory-utilization", type=float, default=0.9)
@@ -526,8 +576,14 @@ def main():
                           gpu_memory_utilization=args.gpu_memory_utilization,
                           swap_space=args.swap_space,
                           num_gpu_blocks_override=args.num_gpu_blocks)
+    arrivals = None
+    if args.request_rate is not None:
+        arrivals = make_arrivals(len(reqs), args.request_rate, args.cv)
+        if args.request_time is not None:
+            keep = int(np.searchsorted(arrivals, args.request_time, side="right"))
+            reqs, arrivals = reqs[:keep], arrivals[:keep]
     out = run_trace(llm, reqs, scores=args.scores, record_schedule=args.record,
-                    logprobs=args.logprobs, max_steps=args.max_steps,
+                    logprobs=args.logprobs, max_steps=args.max_steps, arrivals=arrivals,
                     profile=((int(args.profile.split(":")[0]), int(args.profile.split(":")[1]),
                               args.profile.split(":", 2)[2]) if args.profile else None))
     out["engine"] = info

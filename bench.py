@@ -1079,8 +1079,9 @@ def _main(out):
                       "metric": "output tokens/s and p50 request latency from arrival"}
                 for label, arm in arms:
                     left = budget_left()
-                    if left < 150:
-                        tp[label] = {"skipped": f"time budget ({args.extras_budget_s:.0f} s) spent"}
+                    if left < 0.5 * args.extras_budget_s:     # last leg: only in the first half
+                        tp[label] = {"skipped": "more than half of the time budget "
+                                                f"({args.extras_budget_s:.0f} s) spent"}
                         continue
                     tp[label] = run_trace_arm(arm, args, clocks2, min(left, 150.0), poisson=True)
                 if "p50_latency_s" in tp.get("ours", {}) and "p50_latency_s" in tp.get("ref_cuda", {}):

@@ -361,14 +361,15 @@ class B200AuxModel:
     that calls ``set_aux_model_score`` on each group (aux_llm_engine.py:332-412).
 
     A burst of new requests (10 000 at t=0 in the synthetic trace) is scored in chunks of
-    ``chunk_prompts`` prompts: the forward of a chunk is only enqueued, so the GPU runs it while
-    the host tokenises and packs the next one; the scores are read back once, after the last
-    chunk (one device synchronisation per call, as before)."""
+    ``chunk_prompts`` prompts (2048: smaller tokeniser calls lose parallel efficiency,
+    profiles/r02_predictor_host_pipeline.txt): the forward of a chunk is only enqueued, so the
+    GPU runs it while the host tokenises and packs the next one; the scores are read back once,
+    after the last chunk (one device synchronisation per call, as before)."""
 
     def __init__(self, predictor: OPTPredictor, tokenizer: Callable[[str], List[int]],
                  max_length: int = 2048,
                  batch_tokenizer: Optional[Callable[[List[str]], List[List[int]]]] = None,
-                 chunk_prompts: int = 1024):
+                 chunk_prompts: int = 2048):
         self.predictor = predictor
         self.tokenizer = tokenizer
         self.batch_tokenizer = batch_tokenizer

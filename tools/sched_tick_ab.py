@@ -7,7 +7,6 @@ Needs /root/reference.
 
     python tools/sched_tick_ab.py <git-rev> >> profiles/r02_scheduler_tick_v2.txt
 """
-import logging
 import os
 import subprocess
 import sys

@@ -158,3 +158,38 @@ def test_classification_head_and_aux_model(P):
     assert [g.aux_model_score for g in groups] == ret
     assert max(abs(a - b) for a, b in zip(ret, want)) <= 2e-2
     assert all(float(torch.tensor(x, dtype=torch.float16)) == x for x in ret)   # fp16 floats
+
+
+def test_aux_model_burst_in_chunks(P):
+    """A burst of unscored requests goes through obtain_aux_scores in chunks (next chunk tokenised
+    on the helper thread while the forwards of the current one are enqueued, staging ring of
+    three): every group gets the score of ITS prompt - the same, to fp16 round-off of the model,
+    as in one chunk and as the oracle's (stated tolerance 2e-2, see the module docstring)."""
+    class Seq:
+        def __init__(self, text):
+            self.prompt = text
+
+    class Group:
+        def __init__(self, text):
+            self.seqs_dict = {0: Seq(text)}
+            self.aux_model_score = None
+
+        def need_aux_model_score(self):
+            return self.aux_model_score is None
+
+        def set_aux_model_score(self, s):
+            self.aux_model_score = s
+
+    cfg, sd = O.random_opt("125m", seed=6, vocab=1000, max_pos=64, layers=1)
+    tok = lambda text: [2] + [3 + (ord(ch) * 7 + i) % 900 for i, ch in enumerate(text)]
+    texts = [("scheduling by rank " * 3)[: 2 + (11 * i) % 47] + chr(97 + i % 26) for i in range(41)]
+    pred = P.OPTPredictor(cfg, sd, device=DEV, max_batch_tokens=256)    # several forwards per chunk
+    batch = lambda ts: [tok(t) for t in ts]
+    whole = P.B200AuxModel(pred, tok, max_length=40, batch_tokenizer=batch, chunk_prompts=1000)
+    parts = P.B200AuxModel(pred, tok, max_length=40, batch_tokenizer=batch, chunk_prompts=6)
+    ga, gb = [Group(t) for t in texts], [Group(t) for t in texts]
+    a, b = whole.obtain_aux_scores(ga), parts.obtain_aux_scores(gb)
+    assert [g.aux_model_score for g in gb] == b and len(b) == len(texts)
+    want = O.opt_scores(cfg, sd, [tok(t)[:40] for t in texts])
+    assert max(abs(x - y) for x, y in zip(a, b)) <= 2e-2
+    assert max(abs(x - y) for x, y in zip(b, want)) <= 2e-2

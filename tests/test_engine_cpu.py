@@ -123,3 +123,43 @@ def test_trace_with_poisson_arrivals_through_engine(env, monkeypatch):
         # the requests trickled in: the first steps saw only a few of them
         assert seen_live[0] < n // 2 and max(seen_live) > seen_live[0]
     assert res[False]["generated_tokens"] == res[True]["generated_tokens"]
+
+
+def test_engine_trace_cli_with_request_rate(env, monkeypatch, tmp_path):
+    """The command line bench.py's `trace_poisson` leg issues (tools/engine_trace.py --request-rate
+    --request-time --max-output --stop-after 0), with the engine construction replaced by the fake
+    executor: the arrival window cuts the trace, every kept request finishes, the JSON carries
+    what bench.py reads."""
+    import json
+    import sys
+    E, assets = env
+    made = {}
+
+    def fake_build(arm, a, num_stop, **kw):
+        made["stop"] = num_stop
+        llm = F.build_fake_llm(assets, "opt-xxx", gpu_blocks=600, cpu_blocks=32768)
+        llm.llm_engine.scheduler.aux_model = R.StubScorer({})
+        llm.llm_engine.scheduler.aux_model.obtain_aux_scores = lambda sgs: [
+            sg.set_aux_model_score(0.0) for sg in sgs]
+        return llm, {"arm": arm, "init_s": 0.0, "num_gpu_blocks": 600, "num_cpu_blocks": 32768}
+
+    monkeypatch.setattr(E, "bind_arm", lambda arm: None)
+    monkeypatch.setattr(E, "make_assets", lambda *a, **k: assets)
+    monkeypatch.setattr(E, "build_llm", fake_build)
+    monkeypatch.setitem(E.LLAMA, "llama-2-7b", dict(E.LLAMA["llama-tiny"]))
+    out = tmp_path / "poisson.json"
+    monkeypatch.setattr(sys, "argv", [
+        "engine_trace.py", "--arm", "b200", "--model", "llama-2-7b", "--json", str(out),
+        "--num-prompts", "400", "--stop-after", "0", "--request-rate", "300",
+        "--request-time", "0.5", "--max-output", "16"])
+    E.main()
+    d = json.loads(out.read_text())
+    s = d["summary"]
+    assert made["stop"] == 0
+    assert 60 < s["num_requests"] < 300 and s["finished"] == s["num_requests"]
+    assert s["arrivals"].startswith(f"{s['num_requests']} requests over 0.")
+    for k in ("tokens_per_s", "p50_latency_s", "p90_latency_s", "mean_latency_s", "requests_per_s",
+              "generated_tokens", "elapsed_s", "steps", "schedule_s", "execute_model_s",
+              "predictor_s", "other_host_s", "add_requests_s"):
+        assert k in s, k
+    assert d["engine"]["num_gpu_blocks"] == 600 and d["config"]["request_rate"] == 300.0

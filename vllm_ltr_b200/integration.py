@@ -46,7 +46,8 @@ def install_engine(engine, scheduler: bool = True, predictor: bool = True, swap:
         if sched is not None and st.startswith("opt"):
             from . import ltr_scheduler
             ltr_scheduler.install(sched)
-            done["scheduler"] = "LTR tick: CUDA rank kernel + host logic per running request (scheduler.py:969-1502)"
+            done["scheduler"] = ("LTR tick: CUDA rank kernel + host logic per running request "
+                                 "(scheduler.py:969-1502)")
         else:
             done["scheduler"] = f"skipped: schedule_type {st!r} is not an LTR ('opt*') policy"
 
